@@ -1,0 +1,194 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes front-end for oracle/_ref/libwrt_ref.so.
+
+The library is the UNMODIFIED reference renderer (compiled by oracle/Makefile from
+/root/reference) behind the small C harness in oracle/ref_harness.cpp.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "libwrt_ref.so")
+REF_ROOT = "/root/reference/Winmad-s-raytracer-v1.0"
+
+_lib = None
+
+
+def available():
+    return os.path.exists(REF_SO)
+
+
+def lib():
+    """Load the reference library (its static initialisers create debug_bpt.txt in cwd, so load
+    it from a scratch directory)."""
+    global _lib
+    if _lib is None:
+        cwd = os.getcwd()
+        scratch = tempfile.mkdtemp(prefix="wrt_ref_")
+        os.chdir(scratch)
+        try:
+            _lib = C.CDLL(REF_SO)
+        finally:
+            os.chdir(cwd)
+        _lib.ref_create.restype = C.c_void_p
+        _lib.ref_traverse_calls.restype = C.c_ulonglong
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def fixed_torus_scene(dst_dir=None):
+    """torus.scene with its absolute Windows OBJ paths rewritten to the bundled ObjFiles
+    (SURVEY.md §8c).  torus_mirror.obj does not exist and silently contributes no geometry."""
+    import re
+    src = open(os.path.join(REF_ROOT, "torus.scene")).read()
+    out = re.sub(r'path="[^"]*\\\\(torus_[a-z]+\.obj)"',
+                 lambda m: 'path="%s/ObjFiles/%s"' % (REF_ROOT, m.group(1)), src)
+    dst_dir = dst_dir or tempfile.mkdtemp(prefix="wrt_scene_")
+    p = os.path.join(dst_dir, "torus_fixed.scene")
+    open(p, "w").write(out)
+    return p
+
+
+class RefScene:
+    """One reference integrator (+ its Scene).  kind: 'pt' or 'bdpt'."""
+
+    def __init__(self, kind="pt"):
+        self.L = lib()
+        self.kind = kind
+        self.h = C.c_void_p(self.L.ref_create(0 if kind == "pt" else 1))
+        self.width = self.height = 0
+
+    # -- construction -------------------------------------------------------------------------
+    def load_file(self, path, width, height):
+        self.width, self.height = width, height
+        return self.L.ref_load_scene_file(self.h, path.encode(), width, height)
+
+    def build(self, materials, kind, data9, matid, lights12, cam12, width, height):
+        materials = np.ascontiguousarray(materials, np.float32).reshape(-1, 11)
+        kind = np.ascontiguousarray(kind, np.int32)
+        data9 = np.ascontiguousarray(data9, np.float32).reshape(-1, 9)
+        matid = np.ascontiguousarray(matid, np.int32)
+        lights12 = np.ascontiguousarray(lights12, np.float32).reshape(-1, 12)
+        cam12 = np.ascontiguousarray(cam12, np.float32)
+        self.width, self.height = width, height
+        return self.L.ref_build_scene(self.h, len(materials), _fp(materials), len(kind), _ip(kind),
+                                      _fp(data9), _ip(matid), len(lights12), _fp(lights12),
+                                      _fp(cam12), width, height)
+
+    # -- getters ------------------------------------------------------------------------------
+    def prims(self):
+        n = self.L.ref_num_prims(self.h)
+        kind = np.zeros(n, np.int32); data = np.zeros((n, 9), np.float32); mat = np.zeros(n, np.int32)
+        self.L.ref_get_prims(self.h, _ip(kind), _fp(data), _ip(mat))
+        return kind, data, mat
+
+    def prim_boxes(self):
+        n = self.L.ref_num_prims(self.h)
+        b = np.zeros((n, 6), np.float32)
+        self.L.ref_get_prim_boxes(self.h, _fp(b))
+        return b
+
+    def materials(self):
+        n = self.L.ref_num_materials(self.h)
+        m = np.zeros((n, 11), np.float32)
+        self.L.ref_get_materials(self.h, _fp(m))
+        return m
+
+    def lights(self):
+        n = self.L.ref_num_lights(self.h)
+        l = np.zeros((n, 22), np.float32)
+        self.L.ref_get_lights(self.h, _fp(l))
+        return l
+
+    def camera(self):
+        c = np.zeros(45, np.float32)
+        self.L.ref_get_camera(self.h, _fp(c))
+        return c
+
+    def scene_sphere(self):
+        s = np.zeros(5, np.float32)
+        self.L.ref_get_scene_sphere(self.h, _fp(s))
+        return s
+
+    def tree(self):
+        nn = C.c_longlong(); nr = C.c_longlong(); dep = C.c_int(); dmax = C.c_int()
+        self.L.ref_tree_stats(self.h, C.byref(nn), C.byref(nr), C.byref(dep), C.byref(dmax))
+        nn, nr = nn.value, nr.value
+        t = dict(axis=np.zeros(nn, np.int32), split=np.zeros(nn, np.float32),
+                 left=np.zeros(nn, np.int32), right=np.zeros(nn, np.int32),
+                 first_ref=np.zeros(nn, np.int32), nref=np.zeros(nn, np.int32),
+                 box=np.zeros((nn, 6), np.float32), refs=np.zeros(max(nr, 1), np.int32))
+        self.L.ref_tree_flatten(self.h, _ip(t["axis"]), _fp(t["split"]), _ip(t["left"]),
+                                _ip(t["right"]), _ip(t["first_ref"]), _ip(t["nref"]),
+                                _fp(t["box"]), _ip(t["refs"]))
+        t["refs"] = t["refs"][:nr]
+        t["depth"] = dep.value; t["depmax"] = dmax.value
+        return t
+
+    # -- queries ------------------------------------------------------------------------------
+    def intersect(self, rays8, full=False):
+        rays8 = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)
+        n = len(rays8)
+        prim = np.zeros(n, np.int32); t = np.zeros(n, np.float32)
+        if not full:
+            self.L.ref_intersect(self.h, _fp(rays8), C.c_longlong(n), _ip(prim), _fp(t),
+                                 None, None, None, None)
+            return prim, t
+        p = np.zeros((n, 3), np.float32); nn = np.zeros((n, 3), np.float32)
+        ins = np.zeros(n, np.int32); mat = np.zeros(n, np.int32)
+        self.L.ref_intersect(self.h, _fp(rays8), C.c_longlong(n), _ip(prim), _fp(t), _fp(p), _fp(nn),
+                             _ip(ins), _ip(mat))
+        return prim, t, p, nn, ins, mat
+
+    def occluded(self, q9):
+        q9 = np.ascontiguousarray(q9, np.float32).reshape(-1, 9)
+        occ = np.zeros(len(q9), np.uint8)
+        self.L.ref_occluded(self.h, _fp(q9), C.c_longlong(len(q9)),
+                            occ.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return occ
+
+    def generate_rays(self, xy):
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        r = np.zeros((len(xy), 8), np.float32)
+        self.L.ref_generate_rays(self.h, _fp(xy), C.c_longlong(len(xy)), _fp(r))
+        return r
+
+    def render_pt(self, spp, max_depth, seed=5489):
+        f = np.zeros((self.height, self.width, 3), np.float32)
+        assert self.L.ref_render_pt(self.h, spp, max_depth, C.c_uint(seed), _fp(f)) == 0
+        return f
+
+    def render_pt_rows(self, spp, max_depth, seed, row0, row1, col0, col1, want_film=True):
+        f = np.zeros((self.height, self.width, 3), np.float32) if want_film else None
+        assert self.L.ref_render_pt_rows(self.h, spp, max_depth, C.c_uint(seed), row0, row1, col0,
+                                         col1, _fp(f) if want_film else None) == 0
+        return f
+
+    def render_bdpt(self, iterations, seed=5489, control_length=3, max_path_length=10):
+        f = np.zeros((self.height, self.width, 3), np.float32)
+        assert self.L.ref_render_bdpt(self.h, iterations, C.c_uint(seed), control_length,
+                                      max_path_length, _fp(f)) == 0
+        return f
+
+    def traverse_calls(self):
+        return int(self.L.ref_traverse_calls())
+
+    def reset_traverse_calls(self):
+        self.L.ref_reset_traverse_calls()
+
+
+def make_rays(od6):
+    od6 = np.ascontiguousarray(od6, np.float32).reshape(-1, 6)
+    r = np.zeros((len(od6), 8), np.float32)
+    lib().ref_make_rays(_fp(od6), C.c_longlong(len(od6)), _fp(r))
+    return r
