@@ -1,0 +1,144 @@
+// TEST-ONLY library ("hostsim"): the product's __host__ __device__ per-ray / per-path code
+// (csrc/traverse.cuh, pt_logic.cuh, bdpt_logic.cuh) compiled for the CPU with
+// g++ -ffp-contract=off and driven by plain loops.  It lets `pytest -m "not gpu"` check the control
+// flow and arithmetic of the CUDA kernels against the oracle on a box with no GPU.  It is NOT part of
+// libwrt_b200.so, is never imported by the product package, and is not a CPU fallback.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "scene_layout.h"
+#include "pt_logic.cuh"
+#ifdef WRT_HOSTSIM_BDPT
+#include "bdpt_logic.cuh"
+#endif
+
+using namespace wrt;
+
+namespace wrt { void set_error(const std::string&) {} }
+
+struct HsScene { SceneLayout L; };
+
+static void cam_fill(const wrt_camera* c, DevCamera& d)
+{
+    for (int a = 0; a < 3; a++) { d.pos[a] = c->pos[a]; d.forward[a] = c->forward[a]; }
+    d.image_plane_dist = c->image_plane_dist; d.x_res = c->x_res; d.y_res = c->y_res;
+    memcpy(d.r2w, c->raster_to_world, sizeof d.r2w);
+    memcpy(d.w2r, c->world_to_raster, sizeof d.w2r);
+}
+
+extern "C" {
+
+int hs_scene_create(const wrt_scene_desc* d, void** out, char* err256)
+{
+    HsScene* h = new HsScene();
+    std::string err;
+    if (!build_layout(d, h->L, err)) { if (err256) snprintf(err256, 256, "%s", err.c_str()); delete h; return 1; }
+    layout_point_view_at_host(h->L);
+    *out = h;
+    return 0;
+}
+
+void hs_scene_destroy(void* h) { delete (HsScene*)h; }
+
+int hs_num_nodes(void* h) { return ((HsScene*)h)->L.n_nodes; }
+long long hs_num_recs(void* h) { return ((HsScene*)h)->L.n_recs; }
+
+void hs_trace_closest(void* hv, const wrt_ray* rays, size_t n, int pruned, int32_t* prim, float* t)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    for (size_t i = 0; i < n; i++) {
+        RayIn r = { rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz, rays[i].tmin, rays[i].tmax };
+        float tt;
+        prim[i] = pruned ? kd_traverse<true, false>(sc, r, tt, nullptr) : kd_traverse<false, false>(sc, r, tt, nullptr);
+        if (t) t[i] = tt;
+    }
+}
+
+void hs_trace_closest_full(void* hv, const wrt_ray* rays, size_t n, int pruned, int32_t* prim, float* t,
+                           float* p3, float* n3, int32_t* inside, int32_t* matid)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    for (size_t i = 0; i < n; i++) {
+        RayIn r = { rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz, rays[i].tmin, rays[i].tmax };
+        float tt;
+        int id = pruned ? kd_traverse<true, false>(sc, r, tt, nullptr) : kd_traverse<false, false>(sc, r, tt, nullptr);
+        prim[i] = id; t[i] = tt;
+        HitInfo h = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        if (id >= 0) fill_hit(sc, id, r, tt, h);
+        p3[3 * i] = h.px; p3[3 * i + 1] = h.py; p3[3 * i + 2] = h.pz;
+        n3[3 * i] = h.nx; n3[3 * i + 1] = h.ny; n3[3 * i + 2] = h.nz;
+        inside[i] = h.inside; matid[i] = h.matid;
+    }
+}
+
+void hs_trace_occluded(void* hv, const float* q9, size_t n, int pruned, uint8_t* occ)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    for (size_t i = 0; i < n; i++) {
+        const float* q = q9 + 9 * i;
+        RayIn r;
+        make_ray(q[0], q[1], q[2], q[3], q[4], q[5], r);
+        bool vis = pruned ? shadow_visible<true>(sc, r, q[6], q[7], q[8]) : shadow_visible<false>(sc, r, q[6], q[7], q[8]);
+        occ[i] = vis ? 0 : 1;
+    }
+}
+
+void hs_count_visits(void* hv, const wrt_ray* rays, size_t n, int pruned, unsigned long long* out4)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    for (size_t i = 0; i < n; i++) {
+        RayIn r = { rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz, rays[i].tmin, rays[i].tmax };
+        VisitCounters vc = { 0, 0, 0, 0 };
+        float tt;
+        if (pruned) kd_traverse<true, true>(sc, r, tt, &vc); else kd_traverse<false, true>(sc, r, tt, &vc);
+        out4[0] += vc.inner; out4[1] += vc.leaf; out4[2] += vc.tri; out4[3] += vc.sph;
+    }
+}
+
+// Sequential driver of the same pt_generate / pt_shade the CUDA kernels call.
+// rays_out (optional): closest + shadow rays traced.
+void hs_render_pt(void* hv, const wrt_camera* cam, const wrt_pt_params* p, int pruned, float* film,
+                  unsigned long long* rays_out)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    PtParams P;
+    P.width = p->width; P.height = p->height; P.spp = p->spp; P.max_depth = p->max_depth; P.seed = p->seed;
+    P.strata = (int)std::sqrt((double)p->spp); if (P.strata < 1) P.strata = 1;
+    P.sample_first = p->sample_first; P.sample_stride = p->sample_stride > 0 ? p->sample_stride : 1;
+    P.local_spp = (P.spp - P.sample_first + P.sample_stride - 1) / P.sample_stride;
+    P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->spp;
+    P.total_samples = (unsigned long long)P.width * P.height * (unsigned long long)P.local_spp;
+    DevCamera dc; cam_fill(cam, dc);
+    unsigned long long nrays = 0;
+    for (unsigned long long s = 0; s < P.total_samples; s++) {
+        RayIn r; PathData pd;
+        pt_generate(P, dc, s, r, pd);
+        for (;;) {
+            float t;
+            int prim = pruned ? kd_traverse<true, false>(sc, r, t, nullptr) : kd_traverse<false, false>(sc, r, t, nullptr);
+            nrays++;
+            ShadeOut out;
+            pt_shade(sc, P, r, pd, prim, t, out);
+            float* px = film + 3 * (size_t)pd.pixel;
+            if (out.emit) { px[0] += out.emit_c.x * P.film_scale; px[1] += out.emit_c.y * P.film_scale; px[2] += out.emit_c.z * P.film_scale; }
+            if (out.shadow) {
+                RayIn sr;
+                make_ray(out.q[0], out.q[1], out.q[2], out.q[3], out.q[4], out.q[5], sr);
+                nrays++;
+                bool vis = pruned ? shadow_visible<true>(sc, sr, out.q[6], out.q[7], out.q[8]) : shadow_visible<false>(sc, sr, out.q[6], out.q[7], out.q[8]);
+                if (vis) { px[0] += out.shadow_c.x * P.film_scale; px[1] += out.shadow_c.y * P.film_scale; px[2] += out.shadow_c.z * P.film_scale; }
+            }
+            if (!out.alive) break;
+        }
+    }
+    if (rays_out) *rays_out = nrays;
+}
+
+#ifdef WRT_HOSTSIM_BDPT
+void hs_render_bdpt(void* hv, const wrt_camera* cam, const wrt_bdpt_params* p, int pruned, float* film,
+                    unsigned long long* rays_out);
+#endif
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Device-resident scene layout (HBM) shared by all kernels.  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+#include <string>
+#include "hd_compat.h"
+#include "../../include/wrt.h"
+
+namespace wrt {
+
+#define WRT_EPS 1e-3f
+#define WRT_INF 1e7f
+#define WRT_STACK_DEPTH 40      /* reference: depMax + 5 = (int)(1.2 ln N + 2) + 5; 29 at N = 1e8 */
+#define WRT_LEAF_TAG 3u
+
+// KD node, 32 bytes = one L2 sector, two 16-byte loads:
+//   a.x  split plane (interior)            | first leaf record (leaf), as int bits
+//   a.y  (child_pair_index << 2) | axis    | (n_records << 2) | 3
+//   a.z, a.w, b.x : lo.x lo.y lo.z   conservative bounds of every primitive referenced below
+//   b.y, b.z, b.w : hi.x hi.y hi.z
+// Children of an interior node are adjacent: left = pair, right = pair + 1.  Nodes are laid out
+// breadth-first, so the top levels of the tree are the first nodes of the array.
+struct DevNodeHalf { float x, y, z, w; };
+
+// Leaf record, 48 bytes, one per (leaf, primitive) reference, stored in leaf order so a leaf's
+// primitives are contiguous:
+//   triangle: r0 = p0.xyz, prim id   r1 = p0-p1 (A,B,C), 0      r2 = p0-p2 (D,E,F), kind=0
+//   sphere:   r0 = c.xyz,  prim id   r1 = radius, box.l.xyz     r2 = box.r.xyz,     kind=1
+// (p0-p1 and p0-p2 are the same float subtractions Triangle::hit performs first, triangle.cpp:24-30.)
+
+struct DevMaterial {  // Material, R/src/material/material.h:7-31
+    float diffuse[3];
+    float phong[3];
+    float phong_exp;
+    float specular[3];
+    float index;
+    float pad;
+};
+
+struct DevLight {  // AreaLight, R/src/scene/light.h:82-129
+    float p0[3], d1[3], d2[3];
+    float fx[3], fy[3], fz[3];  // localFrame (z = normal)
+    float intensity[3];
+    float inv_area;
+};
+
+struct DevSceneView {  // passed to kernels by value
+    const float4* __restrict__ nodes;      // 2 per node
+    const float4* __restrict__ leaf_recs;  // 3 per leaf reference
+    const float4* __restrict__ prims;      // 3 per primitive: (p0,matid) (p1,kind) (p2,0) | (c,matid) (r,kind..) ..
+    const DevMaterial* __restrict__ materials;
+    const DevLight* __restrict__ lights;
+    int n_nodes, n_prims, n_materials, n_lights;
+    float root_lo[3], root_hi[3];
+    float sphere_center[3], sphere_radius, inv_sphere_radius_sqr;
+};
+
+}  // namespace wrt
+
+#ifdef __CUDACC__
+struct wrt_scene {
+    wrt::DevSceneView view;
+    int device;
+    int traversal_mode;
+    void* d_nodes; void* d_leaf_recs; void* d_prims; void* d_materials; void* d_lights;
+    int64_t n_leaf_recs;
+    wrt_stats stats;
+    // scratch for host-buffer entry points (grown on demand)
+    void* d_scratch_in; size_t scratch_in_bytes;
+    void* d_scratch_out; size_t scratch_out_bytes;
+    unsigned long long* d_counters;  // small device counter block
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    struct wrt_wavefront* wf;        // lazily created integrator state
+};
+
+namespace wrt {
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what);
+#define WRT_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return wrt::cuda_fail(e__, #call); } while (0)
+int ensure_scratch(wrt_scene* sc, size_t in_bytes, size_t out_bytes);
+void wavefront_destroy(wrt_scene* sc);
+}  // namespace wrt
+#endif  // __CUDACC__

@@ -1,0 +1,345 @@
+// Wavefront path tracer: the level-2 entry point wrt_render_pt, a drop-in for
+// SurfaceIntegrator::render + PathIntegrator::raytracing
+// (R/src/surfaceIntegrator/surfaceIntegrator.cpp:14-46, pathIntegrator.cpp:29-148).
+//
+// Organisation: a persistent pool of path slots in HBM.  Each iteration runs three kernels over
+// index queues —
+//   extend : closest-hit traversal of every live path's ray           (the hot kernel)
+//   shade  : one vertex of the bounce loop per live path; emits at most one shadow query;
+//            dead paths are REGENERATED in place from the next camera sample, so the extend queue
+//            stays full until the image is finished (persistent ray queues);
+//   shadow : Scene::occluded for the queued NEE connections, adds unoccluded contributions.
+// Queues are compacted with warp ballot/popc appends (one atomic per warp).  The film is a float
+// H x W x 3 accumulator updated with atomicAdd (several samples of one pixel can be in flight).
+// Every path owns a counter-based RNG keyed on (seed, pixel, global sample index), so the image is
+// independent of pool size, scheduling and of how samples are sharded across GPUs.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include "pt_logic.cuh"
+#include "wavefront.h"
+#include "warp_utils.cuh"
+
+namespace wrt {
+
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ RayIn pool_load_ray(const PathPool& pool, uint32_t slot)
+{
+    const float4* p = reinterpret_cast<const float4*>(pool.ray + slot);
+    const float4 a = p[0], b = p[1];
+    RayIn r;
+    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
+    return r;
+}
+
+__device__ __forceinline__ void pool_store(const PathPool& pool, uint32_t slot, const RayIn& r, const PathData& pd)
+{
+    float4* p = reinterpret_cast<float4*>(pool.ray + slot);
+    p[0] = make_float4(r.ox, r.oy, r.oz, r.dx);
+    p[1] = make_float4(r.dy, r.dz, r.tmin, r.tmax);
+    pool.weight_pdf[slot] = make_float4(pd.weight.x, pd.weight.y, pd.weight.z, pd.last_pdf);
+    pool.meta[slot] = make_uint4(pd.pixel, pd.rng.key, pd.rng.ctr, (uint32_t)pd.length | ((uint32_t)pd.last_specular << 16));
+}
+
+__device__ __forceinline__ void pool_load_data(const PathPool& pool, uint32_t slot, PathData& pd)
+{
+    const float4 w = pool.weight_pdf[slot];
+    const uint4 m = pool.meta[slot];
+    pd.weight = v3(w.x, w.y, w.z); pd.last_pdf = w.w;
+    pd.pixel = m.x; pd.rng.key = m.y; pd.rng.ctr = m.z;
+    pd.length = (int)(m.w & 0xffffu); pd.last_specular = (int)(m.w >> 16);
+}
+
+__device__ __forceinline__ void film_add(float* film, uint32_t pixel, V3 c, float scale)
+{
+    atomicAdd(&film[3 * (size_t)pixel + 0], c.x * scale);
+    atomicAdd(&film[3 * (size_t)pixel + 1], c.y * scale);
+    atomicAdd(&film[3 * (size_t)pixel + 2], c.z * scale);
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0)
+{
+    for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n0; s += gridDim.x * blockDim.x) {
+        RayIn r; PathData pd;
+        pt_generate(P, cam, s, r, pd);
+        pool_store(pool, s, r, pd);
+        queue[s] = s;
+    }
+}
+
+template <bool PRUNED>
+__global__ void __launch_bounds__(kBlock)
+k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters)
+{
+    size_t base;
+    while (next_chunk(&counters[WF_WORK], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        if (e >= n) continue;
+        const uint32_t slot = queue[e];
+        const RayIn r = pool_load_ray(pool, slot);
+        float t;
+        const int prim = kd_traverse<PRUNED, false>(sc, r, t, nullptr);
+        pool.hit_prim[slot] = prim;
+        pool.hit_t[slot] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in, size_t n,
+           uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* counters)
+{
+    size_t base;
+    while (next_chunk(&counters[WF_WORK2], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        const bool valid = e < n;
+        uint32_t slot = 0;
+        RayIn r; PathData pd; ShadeOut out;
+        out.alive = false; out.emit = false; out.shadow = false;
+        if (valid) {
+            slot = queue_in[e];
+            r = pool_load_ray(pool, slot);
+            pool_load_data(pool, slot, pd);
+            pt_shade(sc, P, r, pd, pool.hit_prim[slot], pool.hit_t[slot], out);
+            if (out.emit) film_add(film, pd.pixel, out.emit_c, P.film_scale);
+        }
+        // NEE connection -> shadow queue
+        const unsigned long long spos = warp_append(&counters[WF_SHADOW_COUNT], valid && out.shadow);
+        if (valid && out.shadow) {
+            sq.a[spos] = make_float4(out.q[0], out.q[1], out.q[2], out.shadow_c.x);
+            sq.b[spos] = make_float4(out.q[3], out.q[4], out.q[5], out.shadow_c.y);
+            sq.c[spos] = make_float4(out.q[6], out.q[7], out.q[8], out.shadow_c.z);
+            sq.pixel[spos] = pd.pixel;
+        }
+        // path regeneration: a finished path's slot takes the next camera sample
+        bool alive = valid && out.alive;
+        const bool dead = valid && !out.alive;
+        const unsigned long long snew = warp_append(&counters[WF_NEXT_SAMPLE], dead);
+        if (dead && snew < P.total_samples) {
+            pt_generate(P, cam, snew, r, pd);
+            alive = true;
+        }
+        const unsigned long long qpos = warp_append(&counters[WF_NEXT_COUNT], alive);
+        if (alive) {
+            pool_store(pool, slot, r, pd);
+            queue_out[qpos] = slot;
+        }
+    }
+}
+
+template <bool PRUNED>
+__global__ void __launch_bounds__(kBlock)
+k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters)
+{
+    const size_t n = (size_t)counters[WF_SHADOW_COUNT];
+    size_t base;
+    while (next_chunk(&counters[WF_WORK3], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        if (e >= n) continue;
+        const float4 a = sq.a[e], b = sq.b[e], c = sq.c[e];
+        RayIn r;
+        make_ray(a.x, a.y, a.z, b.x, b.y, b.z, r);
+        if (shadow_visible<PRUNED>(sc, r, c.x, c.y, c.z))
+            film_add(film, sq.pixel[e], v3(a.w, b.w, c.w), scale);
+    }
+}
+
+// ---- wavefront state -------------------------------------------------------------------------------
+int wavefront_get(wrt_scene* sc, int capacity, wrt_wavefront** out)
+{
+    if (sc->wf && sc->wf->capacity >= capacity) { *out = sc->wf; return WRT_OK; }
+    wavefront_destroy(sc);
+    wrt_wavefront* wf = new wrt_wavefront();
+    memset(wf, 0, sizeof *wf);
+    wf->capacity = capacity;
+    sc->wf = wf;
+    const size_t P = (size_t)capacity;
+    WRT_CUDA(cudaMalloc((void**)&wf->pool.ray, P * sizeof(wrt_ray)));
+    WRT_CUDA(cudaMalloc((void**)&wf->pool.weight_pdf, P * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&wf->pool.meta, P * sizeof(uint4)));
+    WRT_CUDA(cudaMalloc((void**)&wf->pool.hit_prim, P * sizeof(int32_t)));
+    WRT_CUDA(cudaMalloc((void**)&wf->pool.hit_t, P * sizeof(float)));
+    WRT_CUDA(cudaMalloc((void**)&wf->queue[0], P * sizeof(uint32_t)));
+    WRT_CUDA(cudaMalloc((void**)&wf->queue[1], P * sizeof(uint32_t)));
+    WRT_CUDA(cudaMalloc((void**)&wf->shadow.a, P * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&wf->shadow.b, P * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&wf->shadow.c, P * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&wf->shadow.pixel, P * sizeof(uint32_t)));
+    WRT_CUDA(cudaMalloc((void**)&wf->counters, WF_COUNTERS * sizeof(unsigned long long)));
+    WRT_CUDA(cudaMallocHost((void**)&wf->h_counters, WF_COUNTERS * sizeof(unsigned long long)));
+    *out = wf;
+    return WRT_OK;
+}
+
+int wavefront_film(wrt_scene* sc, size_t floats, float** out)
+{
+    wrt_wavefront* wf = sc->wf;
+    if (wf->film_floats < floats) {
+        if (wf->film) cudaFree(wf->film);
+        wf->film = nullptr; wf->film_floats = 0;
+        WRT_CUDA(cudaMalloc((void**)&wf->film, floats * sizeof(float)));
+        wf->film_floats = floats;
+    }
+    *out = wf->film;
+    return WRT_OK;
+}
+
+void bdpt_destroy(wrt_wavefront* wf);
+
+void wavefront_destroy(wrt_scene* sc)
+{
+    wrt_wavefront* wf = sc->wf;
+    if (!wf) return;
+    bdpt_destroy(wf);
+    cudaFree(wf->pool.ray); cudaFree(wf->pool.weight_pdf); cudaFree(wf->pool.meta);
+    cudaFree(wf->pool.hit_prim); cudaFree(wf->pool.hit_t);
+    cudaFree(wf->queue[0]); cudaFree(wf->queue[1]);
+    cudaFree(wf->shadow.a); cudaFree(wf->shadow.b); cudaFree(wf->shadow.c); cudaFree(wf->shadow.pixel);
+    cudaFree(wf->counters); cudaFreeHost(wf->h_counters); cudaFree(wf->film);
+    delete wf;
+    sc->wf = nullptr;
+}
+
+void fill_camera(const wrt_camera* c, DevCamera& d)
+{
+    for (int a = 0; a < 3; a++) { d.pos[a] = c->pos[a]; d.forward[a] = c->forward[a]; }
+    d.image_plane_dist = c->image_plane_dist; d.x_res = c->x_res; d.y_res = c->y_res;
+    memcpy(d.r2w, c->raster_to_world, sizeof d.r2w);
+    memcpy(d.w2r, c->world_to_raster, sizeof d.w2r);
+}
+
+static int pool_capacity()
+{
+    const char* e = getenv("WRT_POOL_PATHS");
+    long v = e ? atol(e) : (1L << 21);
+    if (v < 1024) v = 1024;
+    if (v > (1L << 26)) v = 1L << 26;
+    return (int)v;
+}
+
+static int pt_fill_params(const wrt_pt_params* p, PtParams& P)
+{
+    if (!p || p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_depth < 0) {
+        set_error("wrt_render_pt: bad parameters"); return WRT_ERR_INVALID;
+    }
+    P.width = p->width; P.height = p->height; P.spp = p->spp; P.max_depth = p->max_depth; P.seed = p->seed;
+    P.strata = (int)std::sqrt((double)p->spp);
+    if (P.strata < 1) P.strata = 1;
+    P.sample_first = p->sample_first; P.sample_stride = p->sample_stride > 0 ? p->sample_stride : 1;
+    if (P.sample_first < 0 || P.sample_first >= P.spp) { set_error("wrt_render_pt: sample_first out of range"); return WRT_ERR_INVALID; }
+    P.local_spp = (P.spp - P.sample_first + P.sample_stride - 1) / P.sample_stride;
+    P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->spp;
+    P.total_samples = (unsigned long long)P.width * P.height * (unsigned long long)P.local_spp;
+    return WRT_OK;
+}
+
+static int pt_capacity(const PtParams& P)
+{
+    const unsigned long long cap = std::min<unsigned long long>((unsigned long long)pool_capacity(), P.total_samples);
+    return (int)std::max<unsigned long long>(cap, 1024ull);
+}
+
+static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st)
+{
+    if (!cam) { set_error("wrt_render_pt: null camera"); return WRT_ERR_INVALID; }
+    if (sc->view.n_lights <= 0) { set_error("wrt_render_pt: the scene has no light (the reference indexes an empty vector here)"); return WRT_ERR_INVALID; }
+    PtParams P;
+    int rc = pt_fill_params(p, P);
+    if (rc) return rc;
+    DevCamera dc; fill_camera(cam, dc);
+    wrt_wavefront* wf = nullptr;
+    rc = wavefront_get(sc, pt_capacity(P), &wf);
+    if (rc) return rc;
+    const unsigned long long cap = std::min<unsigned long long>((unsigned long long)wf->capacity, P.total_samples);
+    const unsigned n0 = (unsigned)cap;
+    const bool pruned = sc->traversal_mode == WRT_TRAVERSE_PRUNED;
+
+    static int g_init = persistent_grid_for((const void*)k_pt_init, kBlock);
+    static int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
+    static int g_ext_e = persistent_grid_for((const void*)k_pt_extend<false>, kBlock);
+    static int g_shade = persistent_grid_for((const void*)k_pt_shade, kBlock);
+    static int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
+    static int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
+
+    WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
+    k_pt_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0);
+    WRT_CUDA(cudaGetLastError());
+    {
+        unsigned long long first = n0;
+        WRT_CUDA(cudaMemcpyAsync(&wf->counters[WF_NEXT_SAMPLE], &first, sizeof first, cudaMemcpyHostToDevice, st));
+    }
+    sc->stats.kernel_launches += 1;
+    size_t n = n0;
+    int cur = 0;
+    unsigned long long iters = 0;
+    while (n > 0) {
+        WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), st));
+        if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        k_pt_shade<<<g_shade, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
+                                               d_film, wf->counters);
+        if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        WRT_CUDA(cudaGetLastError());
+        WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters, WF_PER_ITER * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        WRT_CUDA(cudaStreamSynchronize(st));
+        sc->stats.closest_rays += n;
+        sc->stats.shadow_rays += wf->h_counters[WF_SHADOW_COUNT];
+        sc->stats.kernel_launches += 3;
+        n = (size_t)wf->h_counters[WF_NEXT_COUNT];
+        cur ^= 1;
+        if (++iters > (1ull << 32)) { set_error("wrt_render_pt: runaway iteration count"); return WRT_ERR_CUDA; }
+    }
+    sc->stats.samples += P.total_samples;
+    return WRT_OK;
+}
+
+}  // namespace wrt
+
+using namespace wrt;
+
+extern "C" {
+
+int wrt_render_pt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, void* stream)
+{
+    if (!sc || !d_film) { set_error("wrt_render_pt_dev: null argument"); return WRT_ERR_INVALID; }
+    WRT_CUDA(cudaSetDevice(sc->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    int rc = render_pt_device(sc, cam, p, d_film, st);
+    if (rc) return rc;
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_render_ms = ms;
+    return WRT_OK;
+}
+
+int wrt_render_pt(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* film)
+{
+    if (!sc || !film || !p) { set_error("wrt_render_pt: null argument"); return WRT_ERR_INVALID; }
+    WRT_CUDA(cudaSetDevice(sc->device));
+    PtParams P;
+    int rc = pt_fill_params(p, P);
+    if (rc) return rc;
+    wrt_wavefront* wf = nullptr;
+    rc = wavefront_get(sc, pt_capacity(P), &wf);   // grow the pool first: re-creating it frees the film
+    if (rc) return rc;
+    const size_t floats = (size_t)p->width * p->height * 3;
+    float* d_film = nullptr;
+    rc = wavefront_film(sc, floats, &d_film);
+    if (rc) return rc;
+    cudaStream_t st = sc->stream;
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    WRT_CUDA(cudaMemsetAsync(d_film, 0, floats * sizeof(float), st));
+    rc = render_pt_device(sc, cam, p, d_film, st);
+    if (rc) return rc;
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaMemcpyAsync(film, d_film, floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_render_ms = ms;
+    return WRT_OK;
+}
+
+}  // extern "C"

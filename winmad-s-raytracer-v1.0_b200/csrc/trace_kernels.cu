@@ -1,0 +1,322 @@
+// Level-1 ray queries behind the C ABI: batch equivalents of Scene::intersect(ray,inter),
+// Scene::intersect(ray), Scene::shadowRayTest and Scene::occluded (R/src/scene/scene.cpp:21-81).
+//
+// Launch shape: persistent warps.  The grid is (SM count x resident blocks per SM); each warp pulls
+// the next 32 consecutive rays from a global counter until the batch is exhausted, so long and short
+// rays balance across the machine without a tail of idle SMs.  One thread = one ray; the per-thread
+// traversal stack lives in local memory (L1-resident, lane-interleaved).
+#include <string>
+#include "traverse.cuh"
+#include "warp_utils.cuh"
+
+namespace wrt {
+
+constexpr int kTraceBlock = 128;
+
+__device__ __forceinline__ RayIn load_ray(const wrt_ray* rays, size_t i)
+{
+    const float4* p = reinterpret_cast<const float4*>(rays + i);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    RayIn r;
+    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
+    return r;
+}
+
+template <bool PRUNED>
+__global__ void __launch_bounds__(kTraceBlock)
+k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int32_t* __restrict__ prim,
+                float* __restrict__ t_out, float* __restrict__ p3, float* __restrict__ n3,
+                int32_t* __restrict__ inside, int32_t* __restrict__ matid, unsigned long long* counter)
+{
+    size_t base;
+    while (next_chunk(counter, n, base)) {
+        const size_t i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        const RayIn r = load_ray(rays, i);
+        float t;
+        const int id = kd_traverse<PRUNED, false>(sc, r, t, nullptr);
+        prim[i] = id;
+        if (t_out) t_out[i] = t;
+        if (p3 || n3 || inside || matid) {
+            HitInfo h = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0, 0 };
+            if (id >= 0) fill_hit(sc, id, r, t, h);
+            if (p3) { p3[3 * i] = h.px; p3[3 * i + 1] = h.py; p3[3 * i + 2] = h.pz; }
+            if (n3) { n3[3 * i] = h.nx; n3[3 * i + 1] = h.ny; n3[3 * i + 2] = h.nz; }
+            if (inside) inside[i] = h.inside;
+            if (matid) matid[i] = h.matid;
+        }
+    }
+}
+
+template <bool PRUNED>
+__global__ void __launch_bounds__(kTraceBlock)
+k_trace_any(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ hit,
+            unsigned long long* counter)
+{
+    size_t base;
+    while (next_chunk(counter, n, base)) {
+        const size_t i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        const RayIn r = load_ray(rays, i);
+        float t;
+        hit[i] = kd_traverse<PRUNED, false>(sc, r, t, nullptr) >= 0 ? 1 : 0;
+    }
+}
+
+// shadowRayTest: ray given, target point given; visible = 1.0f / 0.0f
+template <bool PRUNED>
+__global__ void __launch_bounds__(kTraceBlock)
+k_trace_shadow(DevSceneView sc, const wrt_ray* __restrict__ rays, const float* __restrict__ target3, size_t n,
+               float* __restrict__ visible, unsigned long long* counter)
+{
+    size_t base;
+    while (next_chunk(counter, n, base)) {
+        const size_t i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        const RayIn r = load_ray(rays, i);
+        visible[i] = shadow_visible<PRUNED>(sc, r, target3[3 * i], target3[3 * i + 1], target3[3 * i + 2]) ? 1.0f : 0.0f;
+    }
+}
+
+// occluded(p1, dir, p2): builds Ray(p1, dir) (normalising dir) and negates shadowRayTest
+template <bool PRUNED>
+__global__ void __launch_bounds__(kTraceBlock)
+k_trace_occluded(DevSceneView sc, const float* __restrict__ q9, size_t n, uint8_t* __restrict__ occluded,
+                 unsigned long long* counter)
+{
+    size_t base;
+    while (next_chunk(counter, n, base)) {
+        const size_t i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        const float* q = q9 + 9 * i;
+        RayIn r;
+        make_ray(q[0], q[1], q[2], q[3], q[4], q[5], r);
+        occluded[i] = shadow_visible<PRUNED>(sc, r, q[6], q[7], q[8]) ? 0 : 1;
+    }
+}
+
+__global__ void __launch_bounds__(kTraceBlock)
+k_count_visits(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, unsigned long long* counter,
+               unsigned long long* sums /* inner, leaf, tri, sph */)
+{
+    size_t base;
+    unsigned long long a = 0, b = 0, c = 0, d = 0;
+    while (next_chunk(counter, n, base)) {
+        const size_t i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+        const RayIn r = load_ray(rays, i);
+        VisitCounters vc = { 0u, 0u, 0u, 0u };
+        float t;
+        kd_traverse<false, true>(sc, r, t, &vc);
+        a += vc.inner; b += vc.leaf; c += vc.tri; d += vc.sph;
+    }
+    atomicAdd(&sums[0], a); atomicAdd(&sums[1], b); atomicAdd(&sums[2], c); atomicAdd(&sums[3], d);
+}
+
+int persistent_grid_for(const void* kernel, int block)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+// d_counters layout: [0] work counter, [8..11] visit sums
+static int launch_closest(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_t* d_prim, float* d_t,
+                          float* d_p, float* d_n, int32_t* d_inside, int32_t* d_matid, cudaStream_t st)
+{
+    if (n == 0) return WRT_OK;
+    WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
+    if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
+        static int grid = persistent_grid_for((const void*)k_trace_closest<true>, kTraceBlock);
+        k_trace_closest<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, sc->d_counters);
+    } else {
+        static int grid = persistent_grid_for((const void*)k_trace_closest<false>, kTraceBlock);
+        k_trace_closest<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, sc->d_counters);
+    }
+    WRT_CUDA(cudaGetLastError());
+    sc->stats.closest_rays += n;
+    sc->stats.kernel_launches += 1;
+    return WRT_OK;
+}
+
+static int launch_occluded(wrt_scene* sc, const float* d_q9, size_t n, uint8_t* d_occ, cudaStream_t st)
+{
+    if (n == 0) return WRT_OK;
+    WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
+    if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
+        static int grid = persistent_grid_for((const void*)k_trace_occluded<true>, kTraceBlock);
+        k_trace_occluded<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, sc->d_counters);
+    } else {
+        static int grid = persistent_grid_for((const void*)k_trace_occluded<false>, kTraceBlock);
+        k_trace_occluded<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, sc->d_counters);
+    }
+    WRT_CUDA(cudaGetLastError());
+    sc->stats.shadow_rays += n;
+    sc->stats.kernel_launches += 1;
+    return WRT_OK;
+}
+
+}  // namespace wrt
+
+using namespace wrt;
+
+#define CHECK_SCENE(sc) do { if (!(sc)) { set_error("null scene"); return WRT_ERR_INVALID; } \
+    WRT_CUDA(cudaSetDevice((sc)->device)); } while (0)
+
+extern "C" {
+
+int wrt_trace_closest_full(wrt_scene* sc, const wrt_ray* rays, size_t n, int32_t* prim, float* t,
+                           float* p3, float* n3, int32_t* inside, int32_t* matid)
+{
+    CHECK_SCENE(sc);
+    if (n == 0) return WRT_OK;
+    if (!rays || !prim) { set_error("wrt_trace_closest: null buffer"); return WRT_ERR_INVALID; }
+    // scratch out: prim(4) t(4) p(12) n(12) inside(4) matid(4) per ray
+    int rc = ensure_scratch(sc, n * sizeof(wrt_ray), n * 40);
+    if (rc) return rc;
+    char* o = (char*)sc->d_scratch_out;
+    int32_t* d_prim = (int32_t*)o; float* d_t = (float*)(o + 4 * n);
+    float* d_p = p3 ? (float*)(o + 8 * n) : nullptr; float* d_n = n3 ? (float*)(o + 20 * n) : nullptr;
+    int32_t* d_in = inside ? (int32_t*)(o + 32 * n) : nullptr; int32_t* d_m = matid ? (int32_t*)(o + 36 * n) : nullptr;
+    cudaStream_t st = sc->stream;
+    WRT_CUDA(cudaMemcpyAsync(sc->d_scratch_in, rays, n * sizeof(wrt_ray), cudaMemcpyHostToDevice, st));
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    rc = launch_closest(sc, (const wrt_ray*)sc->d_scratch_in, n, d_prim, d_t, d_p, d_n, d_in, d_m, st);
+    if (rc) return rc;
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaMemcpyAsync(prim, d_prim, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (t) WRT_CUDA(cudaMemcpyAsync(t, d_t, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (p3) WRT_CUDA(cudaMemcpyAsync(p3, d_p, 12 * n, cudaMemcpyDeviceToHost, st));
+    if (n3) WRT_CUDA(cudaMemcpyAsync(n3, d_n, 12 * n, cudaMemcpyDeviceToHost, st));
+    if (inside) WRT_CUDA(cudaMemcpyAsync(inside, d_in, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (matid) WRT_CUDA(cudaMemcpyAsync(matid, d_m, 4 * n, cudaMemcpyDeviceToHost, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    sc->stats.last_trace_ms = ms;
+    return WRT_OK;
+}
+
+int wrt_trace_closest(wrt_scene* sc, const wrt_ray* rays, size_t n, int32_t* prim, float* t)
+{
+    return wrt_trace_closest_full(sc, rays, n, prim, t, nullptr, nullptr, nullptr, nullptr);
+}
+
+int wrt_trace_any(wrt_scene* sc, const wrt_ray* rays, size_t n, uint8_t* hit)
+{
+    CHECK_SCENE(sc);
+    if (n == 0) return WRT_OK;
+    if (!rays || !hit) { set_error("wrt_trace_any: null buffer"); return WRT_ERR_INVALID; }
+    int rc = ensure_scratch(sc, n * sizeof(wrt_ray), n);
+    if (rc) return rc;
+    cudaStream_t st = sc->stream;
+    WRT_CUDA(cudaMemcpyAsync(sc->d_scratch_in, rays, n * sizeof(wrt_ray), cudaMemcpyHostToDevice, st));
+    WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
+        static int grid = persistent_grid_for((const void*)k_trace_any<true>, kTraceBlock);
+        k_trace_any<true><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, sc->d_counters);
+    } else {
+        static int grid = persistent_grid_for((const void*)k_trace_any<false>, kTraceBlock);
+        k_trace_any<false><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, sc->d_counters);
+    }
+    WRT_CUDA(cudaGetLastError());
+    sc->stats.closest_rays += n; sc->stats.kernel_launches += 1;
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaMemcpyAsync(hit, sc->d_scratch_out, n, cudaMemcpyDeviceToHost, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_trace_ms = ms;
+    return WRT_OK;
+}
+
+int wrt_trace_shadow(wrt_scene* sc, const wrt_ray* rays, const float* target3, size_t n, float* visible)
+{
+    CHECK_SCENE(sc);
+    if (n == 0) return WRT_OK;
+    if (!rays || !target3 || !visible) { set_error("wrt_trace_shadow: null buffer"); return WRT_ERR_INVALID; }
+    int rc = ensure_scratch(sc, n * (sizeof(wrt_ray) + 16), n * 4);  // rays, then targets (16-byte aligned start)
+    if (rc) return rc;
+    cudaStream_t st = sc->stream;
+    char* in = (char*)sc->d_scratch_in;
+    float* d_target = (float*)(in + n * sizeof(wrt_ray));
+    WRT_CUDA(cudaMemcpyAsync(in, rays, n * sizeof(wrt_ray), cudaMemcpyHostToDevice, st));
+    WRT_CUDA(cudaMemcpyAsync(d_target, target3, n * 12, cudaMemcpyHostToDevice, st));
+    WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
+        static int grid = persistent_grid_for((const void*)k_trace_shadow<true>, kTraceBlock);
+        k_trace_shadow<true><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)in, d_target, n, (float*)sc->d_scratch_out, sc->d_counters);
+    } else {
+        static int grid = persistent_grid_for((const void*)k_trace_shadow<false>, kTraceBlock);
+        k_trace_shadow<false><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)in, d_target, n, (float*)sc->d_scratch_out, sc->d_counters);
+    }
+    WRT_CUDA(cudaGetLastError());
+    sc->stats.shadow_rays += n; sc->stats.kernel_launches += 1;
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaMemcpyAsync(visible, sc->d_scratch_out, n * 4, cudaMemcpyDeviceToHost, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_trace_ms = ms;
+    return WRT_OK;
+}
+
+int wrt_trace_occluded(wrt_scene* sc, const float* q9, size_t n, uint8_t* occluded)
+{
+    CHECK_SCENE(sc);
+    if (n == 0) return WRT_OK;
+    if (!q9 || !occluded) { set_error("wrt_trace_occluded: null buffer"); return WRT_ERR_INVALID; }
+    int rc = ensure_scratch(sc, n * 36, n);
+    if (rc) return rc;
+    cudaStream_t st = sc->stream;
+    WRT_CUDA(cudaMemcpyAsync(sc->d_scratch_in, q9, n * 36, cudaMemcpyHostToDevice, st));
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    rc = launch_occluded(sc, (const float*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, st);
+    if (rc) return rc;
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaMemcpyAsync(occluded, sc->d_scratch_out, n, cudaMemcpyDeviceToHost, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_trace_ms = ms;
+    return WRT_OK;
+}
+
+int wrt_trace_closest_dev(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_t* d_prim, float* d_t, void* stream)
+{
+    CHECK_SCENE(sc);
+    if (n == 0) return WRT_OK;
+    if (!d_rays || !d_prim || ((uintptr_t)d_rays & 15)) { set_error("wrt_trace_closest_dev: null or misaligned (16 B) device buffer"); return WRT_ERR_INVALID; }
+    return launch_closest(sc, d_rays, n, d_prim, d_t, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int wrt_trace_occluded_dev(wrt_scene* sc, const float* d_q9, size_t n, uint8_t* d_occ, void* stream)
+{
+    CHECK_SCENE(sc);
+    if (n == 0) return WRT_OK;
+    if (!d_q9 || !d_occ) { set_error("wrt_trace_occluded_dev: null device buffer"); return WRT_ERR_INVALID; }
+    return launch_occluded(sc, d_q9, n, d_occ, (cudaStream_t)stream);
+}
+
+int wrt_trace_count_visits(wrt_scene* sc, const wrt_ray* rays, size_t n)
+{
+    CHECK_SCENE(sc);
+    sc->stats.inner_visits = sc->stats.leaf_visits = sc->stats.tri_tests = sc->stats.sphere_tests = 0;
+    if (n == 0) return WRT_OK;
+    if (!rays) { set_error("wrt_trace_count_visits: null buffer"); return WRT_ERR_INVALID; }
+    int rc = ensure_scratch(sc, n * sizeof(wrt_ray), 0);
+    if (rc) return rc;
+    cudaStream_t st = sc->stream;
+    WRT_CUDA(cudaMemcpyAsync(sc->d_scratch_in, rays, n * sizeof(wrt_ray), cudaMemcpyHostToDevice, st));
+    WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), st));
+    static int grid = persistent_grid_for((const void*)k_count_visits, kTraceBlock);
+    k_count_visits<<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, sc->d_counters, sc->d_counters + 8);
+    WRT_CUDA(cudaGetLastError());
+    sc->stats.kernel_launches += 1;
+    unsigned long long h[4];
+    WRT_CUDA(cudaMemcpyAsync(h, sc->d_counters + 8, sizeof h, cudaMemcpyDeviceToHost, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    sc->stats.inner_visits = h[0]; sc->stats.leaf_visits = h[1]; sc->stats.tri_tests = h[2]; sc->stats.sphere_tests = h[3];
+    return WRT_OK;
+}
+
+}  // extern "C"
