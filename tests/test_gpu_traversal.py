@@ -1,0 +1,133 @@
+"""GPU tier: the CUDA kernels, called through the C ABI (include/wrt.h), against the golden vectors,
+the oracle (compiled reference when it travelled with the repo, else the plain-C port) and themselves
+(EXACT == PRUNED on large batches).  Bar: primitive ids / flags identical, t bit-identical."""
+import numpy as np
+import pytest
+
+import engines
+import scenes
+import util
+
+pytestmark = pytest.mark.gpu
+FIXTURES = ["torus", "cbox_dragon", "bunny"]
+
+
+@pytest.mark.parametrize("pruned", [False, True])
+@pytest.mark.parametrize("name", FIXTURES)
+def test_cuda_matches_golden(wrt, name, pruned):
+    sc, z = scenes.load_fixture(name)
+    engines.check_against_golden(wrt, engines.CudaEngine(wrt, sc, pruned), sc, z)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_cuda_matches_oracle_full_batches(wrt, have_ref, name):
+    """T1 at the full C2 batch size: 512^2 primary rays, 4 NEE queries per hit, secondary rays."""
+    sc, z = scenes.load_fixture(name)
+    oracle = engines.RefEngine(wrt, sc) if have_ref else engines.PortEngine(wrt, sc)
+    cuda = engines.CudaEngine(wrt, sc, True)
+    cam = wrt.Camera.from_ref_array(z["cam45"])
+    rays = wrt.generate_rays(cam, scenes.pixel_centres(512, 512))
+    a, b = cuda.intersect(rays, full=True), oracle.intersect(rays, full=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(util.bits(a[1]), util.bits(b[1]))
+    hit = a[0] >= 0
+    for k in (2, 3):
+        assert np.array_equal(util.bits(a[k][hit]), util.bits(b[k][hit]))
+    assert np.array_equal(a[4][hit], b[4][hit]) and np.array_equal(a[5][hit], b[5][hit])
+    q = scenes.nee_queries(a[2], hit & (a[5] > 0), sc.lights)
+    assert np.array_equal(cuda.occluded(q), oracle.occluded(q))
+    r2 = wrt.make_rays(scenes.bounce_rays(a[2], a[3], hit))
+    c, d = cuda.intersect(r2), oracle.intersect(r2)
+    assert np.array_equal(c[0], d[0]) and np.array_equal(util.bits(c[1]), util.bits(d[1]))
+    # the other query flavours of the seam
+    assert np.array_equal(cuda.scene.intersect_any(rays), (a[0] >= 0).astype(np.uint8))
+    vis = cuda.scene.shadowRayTest(rays[hit][:5000], a[2][hit][:5000])
+    assert np.all(vis == 1.0)     # a ray's own hit point is "visible" (scene.cpp:64-67)
+
+
+@pytest.mark.parametrize("name", ["torus", "small_mixed", "synthetic"])
+def test_cuda_adversarial_vs_port(wrt, name):
+    if name == "torus": sc = scenes.load_fixture(name)[0]
+    elif name == "small_mixed": sc = scenes.small_mixed_scene()
+    else: sc = scenes.synthetic_torus_scene(n=96, width=64, height=64, n_spheres=2000)
+    port = engines.PortEngine(wrt, sc)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 60000))
+    b = port.intersect(rays, full=True)
+    for pruned in (False, True):
+        a = engines.CudaEngine(wrt, sc, pruned).intersect(rays, full=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(util.bits(a[1]), util.bits(b[1]))
+        hit = a[0] >= 0
+        assert np.array_equal(util.bits(a[2][hit]), util.bits(b[2][hit]))
+        assert np.array_equal(util.bits(a[3][hit]), util.bits(b[3][hit]))
+        assert np.array_equal(a[4][hit], b[4][hit]) and np.array_equal(a[5][hit], b[5][hit])
+
+
+@pytest.mark.parametrize("name", ["torus", "cbox_dragon", "bunny", "synthetic_1m"])
+def test_exact_equals_pruned_large(wrt, name):
+    """T1b: >= 1e7 rays per scene (primary at 4 sub-pixel offsets, secondary from the hits, random)."""
+    if name == "synthetic_1m":
+        sc = scenes.synthetic_torus_scene(n=708, width=1920, height=1080)
+        cam = wrt.camera_setup(sc.cam12[0:3], sc.cam12[3:6], sc.cam12[6:9], sc.cam12[9], sc.cam12[10], sc.cam12[11])
+        w, h = 1920, 1080
+    else:
+        sc, z = scenes.load_fixture(name)
+        cam = wrt.Camera.from_ref_array(z["cam45"]); w, h = 512, 512
+    hs = util.host_scene(wrt, sc)
+    scene = wrt.Scene(hs)
+    total = 0
+    rng = np.random.Generator(np.random.PCG64(5))
+    lo = sc.data[sc.kind == 0].reshape(-1, 3).min(0); hi = sc.data[sc.kind == 0].reshape(-1, 3).max(0)
+    batches = []
+    for off in ((0, 0), (.25, .25), (-.25, .4), (.4, -.3)):
+        batches.append(("primary", wrt.generate_rays(cam, scenes.pixel_centres(w, h) + np.float32(off))))
+    n_rand = 3_000_000
+    o = (lo + (hi - lo) * (rng.random((n_rand, 3)) * 1.4 - 0.2)).astype(np.float32)
+    d = rng.normal(size=(n_rand, 3)).astype(np.float32)
+    batches.append(("random", wrt.make_rays(np.concatenate([o, d], 1))))
+    for label, rays in batches:
+        scene.set_traversal(wrt.TRAVERSE_EXACT); a = scene.intersect(rays, full=True)
+        scene.set_traversal(wrt.TRAVERSE_PRUNED); b = scene.intersect(rays)
+        assert np.array_equal(a[0], b[0]), (name, label, int((a[0] != b[0]).sum()))
+        assert np.array_equal(util.bits(a[1]), util.bits(b[1])), (name, label)
+        total += len(rays)
+        if label == "primary":   # secondary rays from these hits, both modes
+            hit = a[0] >= 0
+            for salt in (7, 19, 31):
+                r2 = wrt.make_rays(scenes.bounce_rays(a[2], a[3], hit, salt=salt))
+                scene.set_traversal(wrt.TRAVERSE_EXACT); c = scene.intersect(r2)
+                scene.set_traversal(wrt.TRAVERSE_PRUNED); e = scene.intersect(r2)
+                assert np.array_equal(c[0], e[0]) and np.array_equal(util.bits(c[1]), util.bits(e[1])), (name, "secondary")
+                total += len(r2)
+    assert total >= (1e7 if w > 512 else 4e6)
+
+
+def test_visit_counters_and_stats(wrt):
+    sc, z = scenes.load_fixture("torus")
+    cuda = engines.CudaEngine(wrt, sc, True); port = engines.PortEngine(wrt, sc)
+    cam = wrt.Camera.from_ref_array(z["cam45"])
+    rays = wrt.generate_rays(cam, scenes.pixel_centres(512, 512, step=4))
+    c = cuda.scene.count_visits(rays)
+    assert c == port.port.intersect(rays, count=True)[-1]
+    cuda.scene.reset_stats()
+    cuda.scene.intersect(rays)
+    s = cuda.scene.stats()
+    assert s.closest_rays == len(rays) and s.kernel_launches == 1 and s.last_trace_ms > 0
+
+
+def test_empty_ragged_and_device_pointer_variants(wrt):
+    import torch
+    sc = scenes.small_mixed_scene()
+    cuda = engines.CudaEngine(wrt, sc, True); port = engines.PortEngine(wrt, sc)
+    prim, t = cuda.intersect(np.zeros((0, 8), np.float32))
+    assert len(prim) == 0
+    for n in (1, 31, 33, 1000):                      # ragged sizes around the warp width
+        rays = wrt.make_rays(engines.adversarial_rays(sc, max(n, 8)))[:n]
+        a, b = cuda.intersect(rays), port.intersect(rays)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(util.bits(a[1]), util.bits(b[1]))
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 5000))
+    d_rays = torch.from_numpy(rays).cuda()
+    d_prim = torch.empty(len(rays), dtype=torch.int32, device="cuda"); d_t = torch.empty(len(rays), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    cuda.scene.intersect_dev(d_rays.data_ptr(), len(rays), d_prim.data_ptr(), d_t.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    b = port.intersect(rays)
+    assert np.array_equal(d_prim.cpu().numpy(), b[0]) and np.array_equal(util.bits(d_t.cpu().numpy()), util.bits(b[1]))

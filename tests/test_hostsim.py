@@ -1,0 +1,63 @@
+"""The CUDA kernels' per-ray code (csrc/traverse.cuh) compiled for the CPU ("hostsim", test-only) must
+match the golden vectors bit for bit in both traversal modes, and EXACT must equal PRUNED — the same
+checks the GPU tier runs on the real kernels, runnable where there is no GPU."""
+import numpy as np
+import pytest
+
+import engines
+import scenes
+import util
+
+
+@pytest.mark.parametrize("pruned", [False, True])
+@pytest.mark.parametrize("name", ["torus", "cbox_dragon", "bunny"])
+def test_hostsim_matches_golden(wrt, name, pruned):
+    sc, z = scenes.load_fixture(name)
+    engines.check_against_golden(wrt, engines.HostSimEngine(wrt, sc, pruned), sc, z)
+
+
+@pytest.mark.parametrize("name", ["torus", "small_mixed", "synthetic"])
+def test_hostsim_exact_equals_pruned_and_port(wrt, name):
+    if name == "torus": sc = scenes.load_fixture(name)[0]
+    elif name == "small_mixed": sc = scenes.small_mixed_scene()
+    else: sc = scenes.synthetic_torus_scene(n=64, width=64, height=64, n_spheres=500)
+    ex = engines.HostSimEngine(wrt, sc, False); pr = engines.HostSimEngine(wrt, sc, True)
+    port = engines.PortEngine(wrt, sc)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 40000))
+    a, b, c = ex.intersect(rays, full=True), pr.intersect(rays, full=True), port.intersect(rays, full=True)
+    for x in (b, c):
+        assert np.array_equal(a[0], x[0])
+        assert np.array_equal(util.bits(a[1]), util.bits(x[1]))
+        hit = a[0] >= 0
+        assert np.array_equal(util.bits(a[2][hit]), util.bits(x[2][hit]))
+        assert np.array_equal(util.bits(a[3][hit]), util.bits(x[3][hit]))
+        assert np.array_equal(a[4][hit], x[4][hit]) and np.array_equal(a[5][hit], x[5][hit])
+
+
+def test_visit_counters_match_port(wrt):
+    """Reference-semantics work counters (the B_ray inputs of the roofline) agree with the instrumented port."""
+    sc, z = scenes.load_fixture("cbox_dragon")
+    sim = engines.HostSimEngine(wrt, sc, False); port = engines.PortEngine(wrt, sc)
+    cam = wrt.Camera.from_ref_array(z["cam45"])
+    rays = wrt.generate_rays(cam, scenes.pixel_centres(512, 512, step=4))
+    c1 = sim.sim.count_visits(rays, pruned=False)
+    c2 = port.port.intersect(rays, count=True)[-1]
+    assert c1 == c2
+    c3 = sim.sim.count_visits(rays, pruned=True)
+    assert c3["tri"] <= c1["tri"] and c3["leaf"] <= c1["leaf"]
+
+
+def test_empty_and_ragged_inputs(wrt):
+    sc = scenes.small_mixed_scene()
+    e = engines.HostSimEngine(wrt, sc, True)
+    prim, t = e.intersect(np.zeros((0, 8), np.float32))
+    assert len(prim) == 0
+    # rays that miss the root box entirely, rays with zero-length direction (NaN dir after the ctor)
+    od = np.array([[10, 10, 10, 1, 0, 0], [0, 0, 0, 0, 0, 0], [0, -0.5, 0, 0, 1, 0]], np.float32)
+    with np.errstate(all="ignore"):
+        rays = wrt.make_rays(od)
+    prim, t = e.intersect(rays)
+    port = engines.PortEngine(wrt, sc)
+    p2, t2 = port.intersect(rays)
+    assert np.array_equal(prim, p2) and np.array_equal(util.bits(t), util.bits(t2))
+    assert prim[0] == -1 and prim[2] >= 0

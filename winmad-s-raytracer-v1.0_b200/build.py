@@ -58,7 +58,7 @@ def build(force=False, verbose_ptxas=False):
             _run([CXX] + CXX_FLAGS + ["-I", os.path.dirname(NVCC) + "/../include", "-c", src, "-o", o])
         objs.append(o)
     if force or _newer(LIB, objs):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        _run([NVCC, "-shared", "-o", LIB] + objs)  # nvcc links the static cudart by default
     return LIB
 
 
