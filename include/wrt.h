@@ -110,6 +110,10 @@ typedef struct {
     uint64_t inner_visits, leaf_visits, tri_tests, sphere_tests;
     double last_render_ms;     /* device time of the last wrt_render_* call (CUDA events) */
     double last_trace_ms;      /* device time of the last wrt_trace_* kernel */
+    /* per-stage device time of the last wrt_render_* call (CUDA events around every launch): */
+    double extend_ms, shade_ms, shadow_ms;
+    uint64_t extend_launches;  /* closest-hit (extend) kernel launches in the last render */
+    uint64_t extend_rays;      /* rays those launches traced */
 } wrt_stats;
 
 typedef struct wrt_scene wrt_scene;           /* device-resident scene */
@@ -159,6 +163,9 @@ int wrt_film_write(const char* path, const float* film_hw3, int32_t width, int32
 int wrt_scene_create(const wrt_scene_desc* desc, wrt_scene** out);
 void wrt_scene_destroy(wrt_scene* sc);
 int wrt_scene_set_traversal(wrt_scene* sc, int mode);  /* WRT_TRAVERSE_*; default PRUNED */
+/* Work accounting: when on, the integrators' trace kernels run the EXACT (reference-semantics)
+ * traversal and add their per-ray visit counts to wrt_stats (inner_visits ... sphere_tests). */
+int wrt_scene_set_counting(wrt_scene* sc, int on);
 int wrt_get_stats(wrt_scene* sc, wrt_stats* out);
 int wrt_reset_stats(wrt_scene* sc);
 

@@ -411,7 +411,7 @@ int ref_render_pt(void* hv, int spp, int max_depth, unsigned seed, float* film)
 
 // PathIntegrator on a sub-window of rows [row0,row1) — for bounded CPU-baseline samples.  Same
 // per-pixel body as SurfaceIntegrator::render (R/src/surfaceIntegrator/surfaceIntegrator.cpp:20-41).
-int ref_render_pt_rows(void* hv, int spp, int max_depth, unsigned seed, int row0, int row1,
+int ref_render_pt_rows(void* hv, int spp, int max_depth, unsigned seed, int row0, int row1, int row_stride,
                        int col0, int col1, float* film)
 {
     RefHandle* h = (RefHandle*)hv;
@@ -419,8 +419,9 @@ int ref_render_pt_rows(void* hv, int spp, int max_depth, unsigned seed, int row0
     PathIntegrator* in = h->pt;
     in->samplesPerPixel = spp; in->maxTracingDepth = max_depth;
     in->rng.seed(seed); in->rng.mti = RNG::N;
-    clear_film(in->film);
-    for (int i = row0; i < row1; i++)
+    if (film) clear_film(in->film);
+    if (row_stride < 1) row_stride = 1;
+    for (int i = row0; i < row1; i += row_stride)
         for (int j = col0; j < col1; j++)
             for (int k = 0; k < spp; k++) {
                 Vector3 v0 = Vector3(j - 0.5f, i - 0.5f, 0);
@@ -431,8 +432,7 @@ int ref_render_pt_rows(void* hv, int spp, int max_depth, unsigned seed, int row0
                 Color3 tmp = in->raytracing(ray, 0);
                 in->film->addColor(i, j, tmp);
             }
-    in->film->scale(1.f / spp);
-    if (film) copy_film(in->film, film);
+    if (film) { in->film->scale(1.f / spp); copy_film(in->film, film); }
     return 0;
 }
 

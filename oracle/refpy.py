@@ -168,9 +168,10 @@ class RefScene:
         assert self.L.ref_render_pt(self.h, spp, max_depth, C.c_uint(seed), _fp(f)) == 0
         return f
 
-    def render_pt_rows(self, spp, max_depth, seed, row0, row1, col0, col1, want_film=True):
+    def render_pt_rows(self, spp, max_depth, seed, row0, row1, col0, col1, want_film=True, row_stride=1):
+        """Rows row0, row0+stride, ... < row1, columns [col0, col1): same per-sample body as render()."""
         f = np.zeros((self.height, self.width, 3), np.float32) if want_film else None
-        assert self.L.ref_render_pt_rows(self.h, spp, max_depth, C.c_uint(seed), row0, row1, col0,
+        assert self.L.ref_render_pt_rows(self.h, spp, max_depth, C.c_uint(seed), row0, row1, row_stride, col0,
                                          col1, _fp(f) if want_film else None) == 0
         return f
 

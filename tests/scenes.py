@@ -62,16 +62,21 @@ def displaced_torus(n, R=1.0):
     return np.concatenate([t1, t2]).astype(np.float32)
 
 
-def synthetic_torus_scene(n=708, width=1920, height=1080, n_spheres=0, seed=1, name=None):
-    """C3 (n=708 -> 1 002 528 triangles) / C5 (n=2237 + 100k spheres) style scene: one diffuse mesh on a
-    floor quad, a 2-triangle area light above, optional random spheres."""
+def synthetic_torus_scene(n=708, width=1920, height=1080, n_spheres=0, seed=1, name=None, floor=False):
+    """C3 (n=708 -> 1 002 528 triangles) / C5 (n=2237 + 100k spheres) of SURVEY.md §8d: the displaced
+    torus, one diffuse material, a 2-triangle area light above, optional random spheres.  `floor=True`
+    adds a 2-triangle ground quad; the reference's SAH builder degenerates into x-slabs with such huge
+    primitives (thousands of leaves per ray), so it is off for the benchmark configs."""
     tris = displaced_torus(n)
     floor_z = -0.45
     f = 3.0
-    floor = np.array([[-f, -f, floor_z, f, -f, floor_z, f, f, floor_z],
-                      [-f, -f, floor_z, f, f, floor_z, -f, f, floor_z]], np.float32)
-    data = np.concatenate([tris, floor])
-    matid = np.concatenate([np.full(len(tris), 1, np.int32), np.full(2, 2, np.int32)])
+    data = tris
+    matid = np.full(len(tris), 1, np.int32)
+    if floor:
+        fl = np.array([[-f, -f, floor_z, f, -f, floor_z, f, f, floor_z],
+                       [-f, -f, floor_z, f, f, floor_z, -f, f, floor_z]], np.float32)
+        data = np.concatenate([tris, fl])
+        matid = np.concatenate([matid, np.full(2, 2, np.int32)])
     kind = np.zeros(len(data), np.int32)
     if n_spheres:
         rng = np.random.Generator(np.random.PCG64(seed))

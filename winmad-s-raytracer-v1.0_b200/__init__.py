@@ -81,7 +81,8 @@ class Stats(C.Structure):
     _fields_ = [("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("samples", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("inner_visits", C.c_uint64), ("leaf_visits", C.c_uint64),
                 ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64), ("last_render_ms", C.c_double),
-                ("last_trace_ms", C.c_double)]
+                ("last_trace_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
+                ("shadow_ms", C.c_double), ("extend_launches", C.c_uint64), ("extend_rays", C.c_uint64)]
 
 
 EXPORTS = [
@@ -89,7 +90,8 @@ EXPORTS = [
     "wrt_host_scene_load", "wrt_host_scene_from_arrays", "wrt_host_scene_build_kdtree", "wrt_host_scene_desc",
     "wrt_host_scene_camera", "wrt_host_scene_sphere", "wrt_host_scene_free", "wrt_host_scene_save",
     "wrt_host_scene_load_cache", "wrt_camera_setup", "wrt_camera_generate_rays", "wrt_make_rays",
-    "wrt_film_write", "wrt_scene_create", "wrt_scene_destroy", "wrt_scene_set_traversal", "wrt_get_stats",
+    "wrt_film_write", "wrt_scene_create", "wrt_scene_destroy", "wrt_scene_set_traversal", "wrt_scene_set_counting",
+    "wrt_get_stats",
     "wrt_reset_stats", "wrt_trace_closest", "wrt_trace_closest_full", "wrt_trace_any", "wrt_trace_shadow",
     "wrt_trace_occluded", "wrt_trace_closest_dev", "wrt_trace_occluded_dev", "wrt_trace_count_visits",
     "wrt_render_pt", "wrt_render_pt_dev", "wrt_render_bdpt", "wrt_render_bdpt_dev",
@@ -333,6 +335,9 @@ class Scene:
 
     def set_traversal(self, mode):
         _check(lib().wrt_scene_set_traversal(self._sc, int(mode)), "wrt_scene_set_traversal")
+
+    def set_counting(self, on):
+        _check(lib().wrt_scene_set_counting(self._sc, int(bool(on))), "wrt_scene_set_counting")
 
     def stats(self):
         s = Stats()

@@ -61,6 +61,7 @@ struct wrt_scene {
     wrt::DevSceneView view;
     int device;
     int traversal_mode;
+    int counting;
     void* d_nodes; void* d_leaf_recs; void* d_prims; void* d_materials; void* d_lights;
     int64_t n_leaf_recs;
     wrt_stats stats;

@@ -87,6 +87,55 @@ k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, 
     }
 }
 
+// Counting-mode variants: EXACT traversal with the reference-semantics visit counters.
+__global__ void __launch_bounds__(kBlock)
+k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters)
+{
+    size_t base;
+    unsigned long long a = 0, b = 0, c = 0, d = 0;
+    while (next_chunk(&counters[WF_WORK], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        if (e >= n) continue;
+        const uint32_t slot = queue[e];
+        const RayIn r = pool_load_ray(pool, slot);
+        VisitCounters vc = { 0u, 0u, 0u, 0u };
+        float t;
+        const int prim = kd_traverse<false, true>(sc, r, t, &vc);
+        pool.hit_prim[slot] = prim;
+        pool.hit_t[slot] = t;
+        a += vc.inner; b += vc.leaf; c += vc.tri; d += vc.sph;
+    }
+    atomicAdd(&counters[WF_VISITS + 0], a); atomicAdd(&counters[WF_VISITS + 1], b);
+    atomicAdd(&counters[WF_VISITS + 2], c); atomicAdd(&counters[WF_VISITS + 3], d);
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters)
+{
+    const size_t n = (size_t)counters[WF_SHADOW_COUNT];
+    size_t base;
+    unsigned long long a = 0, b = 0, c = 0, d = 0;
+    while (next_chunk(&counters[WF_WORK3], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        if (e >= n) continue;
+        const float4 qa = sq.a[e], qb = sq.b[e], qc = sq.c[e];
+        RayIn r;
+        make_ray(qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, r);
+        VisitCounters vc = { 0u, 0u, 0u, 0u };
+        float t;
+        const int prim = kd_traverse<false, true>(sc, r, t, &vc);
+        a += vc.inner; b += vc.leaf; c += vc.tri; d += vc.sph;
+        bool vis = prim < 0;
+        if (!vis) {
+            const float ex = (r.ox + r.dx * t) - qc.x, ey = (r.oy + r.dy * t) - qc.y, ez = (r.oz + r.dz * t) - qc.z;
+            vis = !(ex < -WRT_EPS) && !(ex > WRT_EPS) && !(ey < -WRT_EPS) && !(ey > WRT_EPS) && !(ez < -WRT_EPS) && !(ez > WRT_EPS);
+        }
+        if (vis) film_add(film, sq.pixel[e], v3(qa.w, qb.w, qc.w), scale);
+    }
+    atomicAdd(&counters[WF_VISITS + 0], a); atomicAdd(&counters[WF_VISITS + 1], b);
+    atomicAdd(&counters[WF_VISITS + 2], c); atomicAdd(&counters[WF_VISITS + 3], d);
+}
+
 __global__ void __launch_bounds__(kBlock)
 k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in, size_t n,
            uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* counters)
@@ -188,6 +237,31 @@ int wavefront_film(wrt_scene* sc, size_t floats, float** out)
 
 void bdpt_destroy(wrt_wavefront* wf);
 
+int wavefront_events(wrt_wavefront* wf, int n)
+{
+    if (wf->n_ev >= n) return WRT_OK;
+    cudaEvent_t* ne = new cudaEvent_t[n];
+    for (int i = 0; i < wf->n_ev; i++) ne[i] = wf->ev[i];
+    for (int i = wf->n_ev; i < n; i++) WRT_CUDA(cudaEventCreate(&ne[i]));
+    delete[] wf->ev;
+    wf->ev = ne; wf->n_ev = n;
+    return WRT_OK;
+}
+
+// Events are recorded as e[4i] (before extend) e[4i+1] (before shade) e[4i+2] (before shadow) e[4i+3] (after).
+void wavefront_sum_stage_times(wrt_scene* sc, wrt_wavefront* wf, int iters_timed)
+{
+    double ext = 0, shd = 0, shw = 0;
+    for (int i = 0; i < iters_timed; i++) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, wf->ev[4 * i], wf->ev[4 * i + 1]);
+        cudaEventElapsedTime(&b, wf->ev[4 * i + 1], wf->ev[4 * i + 2]);
+        cudaEventElapsedTime(&c, wf->ev[4 * i + 2], wf->ev[4 * i + 3]);
+        ext += a; shd += b; shw += c;
+    }
+    sc->stats.extend_ms = ext; sc->stats.shade_ms = shd; sc->stats.shadow_ms = shw;
+}
+
 void wavefront_destroy(wrt_scene* sc)
 {
     wrt_wavefront* wf = sc->wf;
@@ -198,6 +272,8 @@ void wavefront_destroy(wrt_scene* sc)
     cudaFree(wf->queue[0]); cudaFree(wf->queue[1]);
     cudaFree(wf->shadow.a); cudaFree(wf->shadow.b); cudaFree(wf->shadow.c); cudaFree(wf->shadow.pixel);
     cudaFree(wf->counters); cudaFreeHost(wf->h_counters); cudaFree(wf->film);
+    for (int i = 0; i < wf->n_ev; i++) cudaEventDestroy(wf->ev[i]);
+    delete[] wf->ev;
     delete wf;
     sc->wf = nullptr;
 }
@@ -274,23 +350,48 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     size_t n = n0;
     int cur = 0;
     unsigned long long iters = 0;
+    const int kMaxTimed = 4096;
+    rc = wavefront_events(wf, 4 * 64);
+    if (rc) return rc;
+    int timed = 0;
+    const bool counting = sc->counting != 0;
+    static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count, kBlock);
+    static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count, kBlock);
+    sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
     while (n > 0) {
+        const bool time_it = timed < kMaxTimed;
+        if (time_it && 4 * (timed + 1) > wf->n_ev) { rc = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (rc) return rc; }
+        cudaEvent_t* ev = time_it ? &wf->ev[4 * timed] : nullptr;
         WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), st));
-        if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        if (ev) cudaEventRecord(ev[0], st);
+        if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
         else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        if (ev) cudaEventRecord(ev[1], st);
         k_pt_shade<<<g_shade, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
                                                d_film, wf->counters);
-        if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        if (ev) cudaEventRecord(ev[2], st);
+        if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
         else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        if (ev) { cudaEventRecord(ev[3], st); timed++; }
         WRT_CUDA(cudaGetLastError());
         WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters, WF_PER_ITER * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         WRT_CUDA(cudaStreamSynchronize(st));
         sc->stats.closest_rays += n;
+        sc->stats.extend_launches += 1; sc->stats.extend_rays += n;
         sc->stats.shadow_rays += wf->h_counters[WF_SHADOW_COUNT];
         sc->stats.kernel_launches += 3;
         n = (size_t)wf->h_counters[WF_NEXT_COUNT];
         cur ^= 1;
         if (++iters > (1ull << 32)) { set_error("wrt_render_pt: runaway iteration count"); return WRT_ERR_CUDA; }
+    }
+    wavefront_sum_stage_times(sc, wf, timed);
+    if (counting) {
+        unsigned long long h[4];
+        WRT_CUDA(cudaMemcpyAsync(h, &wf->counters[WF_VISITS], sizeof h, cudaMemcpyDeviceToHost, st));
+        WRT_CUDA(cudaStreamSynchronize(st));
+        sc->stats.inner_visits += h[0]; sc->stats.leaf_visits += h[1]; sc->stats.tri_tests += h[2]; sc->stats.sphere_tests += h[3];
     }
     sc->stats.samples += P.total_samples;
     return WRT_OK;

@@ -128,6 +128,13 @@ int wrt_scene_set_traversal(wrt_scene* sc, int mode)
     return WRT_OK;
 }
 
+int wrt_scene_set_counting(wrt_scene* sc, int on)
+{
+    if (!sc) { set_error("null scene"); return WRT_ERR_INVALID; }
+    sc->counting = on ? 1 : 0;
+    return WRT_OK;
+}
+
 int wrt_get_stats(wrt_scene* sc, wrt_stats* out)
 {
     if (!sc || !out) { set_error("null argument"); return WRT_ERR_INVALID; }

@@ -17,6 +17,7 @@ enum {
     WF_PER_ITER = 8,    // counters [0, WF_PER_ITER) are zeroed before every iteration
     WF_NEXT_SAMPLE = 8, // next camera sample to hand out (path regeneration)
     WF_LIGHT_VERTS = 9,
+    WF_VISITS = 10,     // +0 inner, +1 leaf, +2 tri, +3 sphere (counting mode)
     WF_COUNTERS = 16
 };
 
@@ -48,11 +49,14 @@ struct wrt_wavefront {
     float* film; size_t film_floats;    // library-owned device film for host-buffer entry points
     void* bdpt;                         // BDPT-only buffers (bdpt_wavefront.cu)
     size_t bdpt_bytes;
+    cudaEvent_t* ev; int n_ev;          // stage-timing events (4 per iteration)
 };
 
 namespace wrt {
 int wavefront_get(wrt_scene* sc, int capacity, wrt_wavefront** out);
 int wavefront_film(wrt_scene* sc, size_t floats, float** out);
 int persistent_grid_for(const void* kernel, int block);
+int wavefront_events(wrt_wavefront* wf, int n);
+void wavefront_sum_stage_times(wrt_scene* sc, wrt_wavefront* wf, int iters_timed);
 }
 #endif
