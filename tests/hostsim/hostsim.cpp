@@ -9,9 +9,7 @@
 #include <vector>
 #include "scene_layout.h"
 #include "pt_logic.cuh"
-#ifdef WRT_HOSTSIM_BDPT
 #include "bdpt_logic.cuh"
-#endif
 
 using namespace wrt;
 
@@ -136,9 +134,88 @@ void hs_render_pt(void* hv, const wrt_camera* cam, const wrt_pt_params* p, int p
     if (rays_out) *rays_out = nrays;
 }
 
-#ifdef WRT_HOSTSIM_BDPT
+// Sequential driver of the same bdpt_* functions the CUDA kernels call: BidirPathTracing::runIteration.
+// film: raw accumulator film[a][b] (not transposed), scaled by film_scale (default 1/iterations).
 void hs_render_bdpt(void* hv, const wrt_camera* cam, const wrt_bdpt_params* p, int pruned, float* film,
-                    unsigned long long* rays_out);
-#endif
+                    unsigned long long* rays_out)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    DevCamera dc; cam_fill(cam, dc);
+    BdptParams P;
+    P.width = p->width; P.height = p->height; P.min_len = p->min_path_length; P.max_len = p->max_path_length;
+    P.control_len = p->control_length; P.seed = p->seed;
+    P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->iterations;
+    P.n_paths = (unsigned)(p->width * p->height); P.light_path_num = (float)(p->width * p->height);
+    P.trace_gated = 1;
+    const int stride = p->iter_stride > 0 ? p->iter_stride : 1;
+    const int maxv = P.max_len > 1 ? P.max_len - 1 : 1;
+    unsigned long long nrays = 0;
+    std::vector<LightVertex> verts((size_t)P.n_paths * maxv);
+    std::vector<int> nverts(P.n_paths);
+    auto trace = [&](const RayIn& r, float& t) {
+        nrays++;
+        return pruned ? kd_traverse<true, false>(sc, r, t, nullptr) : kd_traverse<false, false>(sc, r, t, nullptr);
+    };
+    auto visible = [&](const float* q) {
+        RayIn r; make_ray(q[0], q[1], q[2], q[3], q[4], q[5], r);
+        nrays++;
+        return pruned ? shadow_visible<true>(sc, r, q[6], q[7], q[8]) : shadow_visible<false>(sc, r, q[6], q[7], q[8]);
+    };
+    auto add = [&](uint32_t pixel, V3 c) {
+        if (pixel == 0xffffffffu) return;
+        float* px = film + 3 * (size_t)pixel;
+        px[0] += c.x * P.film_scale; px[1] += c.y * P.film_scale; px[2] += c.z * P.film_scale;
+    };
+    for (int it = p->iter_first; it < p->iterations; it += stride) {
+        P.iteration = it;
+        for (uint32_t i = 0; i < P.n_paths; i++) {              // light paths
+            RayIn ray; BdptPath st;
+            bdpt_light_generate(sc, P, i, ray, st);
+            nverts[i] = 0;
+            for (;;) {
+                float t; int prim = trace(ray, t);
+                LightStepOut out;
+                bdpt_light_step(sc, P, dc, ray, st, prim, t, out);
+                if (out.store && nverts[i] < maxv) verts[(size_t)i * maxv + nverts[i]++] = out.v;
+                if (out.connect && visible(out.conn.q)) add(out.conn.pixel, out.conn.c);
+                if (!out.alive) break;
+            }
+        }
+        for (uint32_t i = 0; i < P.n_paths; i++) {              // camera paths
+            RayIn ray; BdptPath st;
+            bdpt_camera_generate(P, dc, i, ray, st);
+            for (;;) {
+                float t; int prim = trace(ray, t);
+                V3 hit, emit_c; Bsdf bsdf; bool emit, has_di; DiEntry di;
+                int k = bdpt_camera_pre(sc, P, ray, st, prim, t, hit, bsdf, emit, emit_c, has_di, di);
+                if (emit) add(st.index, emit_c);
+                if (k == 0) break;
+                if (has_di && visible(di.q)) {
+                    add(di.pixel, di.cA);
+                    if (di.has_B) {
+                        RayIn br; make_ray(di.bo[0], di.bo[1], di.bo[2], di.bd[0], di.bd[1], di.bd[2], br);
+                        float tb; int pb = trace(br, tb);
+                        if (pb >= 0) {
+                            int m = f2i(sc.prims[3 * (size_t)pb].w);
+                            if (m < 0 && -m - 1 == di.light_id) add(di.pixel, di.cB);
+                        }
+                    }
+                }
+                if (k == 1) {
+                    for (int v = 0; v < nverts[i]; v++) {
+                        const LightVertex& lv = verts[(size_t)i * maxv + v];
+                        if (lv.length + 1 + st.length < P.min_len) continue;
+                        if (lv.length + 1 + st.length > P.max_len) break;
+                        Connection c;
+                        if (bdpt_connect_vertices(sc, P, lv, bsdf, hit, st, c) && visible(c.q)) add(c.pixel, c.c);
+                    }
+                }
+                if (!bdpt_sample_scattering(sc, bsdf, hit, ray, st)) break;
+                st.length += 1;
+            }
+        }
+    }
+    if (rays_out) *rays_out = nrays;
+}
 
 }  // extern "C"

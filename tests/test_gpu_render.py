@@ -99,3 +99,46 @@ def test_hostsim_equals_cuda_pt(wrt):
     # libm vs CUDA math differ by ulps; a handful of paths may branch differently
     assert util.rel_rmse(block_mean(gpu, 4), block_mean(cpu, 4)) < 0.02
     assert abs(float(s.closest_rays + s.shadow_rays) - rays) <= 0.002 * rays
+
+
+# ---- BDPT ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cornell", "small_mixed"])
+def test_bdpt_image_parity_with_reference(wrt, have_ref, name):
+    """C4-class: BidirPathTracing with the shipped controlLength = 3 gating, raw (untransposed) film."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    res, iters = 64, 192
+    sc = scenes.cornell_box_scene(res, res) if name == "cornell" else scenes.small_mixed_scene(res, res)
+    hs = util.host_scene(wrt, sc); scene = wrt.Scene(hs); cam = hs.camera()
+    gpu = scene.render_bdpt(cam, wrt.BdptParams(res, res, iters, 0, 10, 3, 9, 0, 1, 0.0, 0))
+    ref = util.ref_scene(sc, "bdpt")
+    ref.reset_traverse_calls()
+    r1 = ref.render_bdpt(iters, seed=5489) / iters; calls = ref.traverse_calls()
+    r2 = ref.render_bdpt(iters, seed=77) / iters
+    rm = (r1 + r2) * 0.5
+    floor = util.rel_rmse(block_mean(r1, 8), block_mean(r2, 8))
+    err = util.rel_rmse(block_mean(gpu, 8), block_mean(rm, 8))
+    s = scene.stats()
+    print("bdpt %s: mean %.5f vs %.5f, rRMSE %.4f floor %.4f, rays/sample %.2f vs %.2f"
+          % (name, gpu.mean(), rm.mean(), err, floor, (s.closest_rays + s.shadow_rays) / s.samples, calls / (res * res * iters)))
+    assert abs(gpu.mean() - rm.mean()) <= 0.01 * rm.mean()
+    assert err <= max(0.01, 1.2 * floor)
+
+
+def test_bdpt_properties(wrt):
+    from hostsim_py import HostSim
+    res = 40
+    sc = scenes.small_mixed_scene(res, res)
+    hs = util.host_scene(wrt, sc); scene = wrt.Scene(hs); cam = hs.camera()
+    p = wrt.BdptParams(res, res, 8, 0, 10, 3, 4, 0, 1, 0.0, 0)
+    a = scene.render_bdpt(cam, p)
+    assert np.isfinite(a).all() and a.min() >= 0 and a.mean() > 0
+    parts = sum(scene.render_bdpt(cam, wrt.shard_bdpt(p, g, 4)) for g in range(4))
+    assert np.allclose(parts, a, rtol=1e-4, atol=1e-6)                   # iteration sharding == 1 call
+    t = scene.render_bdpt(cam, wrt.BdptParams(res, res, 8, 0, 10, 3, 4, 0, 1, 0.0, 1))
+    assert np.allclose(t, a.transpose(1, 0, 2), rtol=1e-4, atol=1e-6)    # outputImage's transpose
+    cpu, rays = HostSim(hs.desc(), hs).render_bdpt(cam, p)
+    assert util.rel_rmse(block_mean(a, 4), block_mean(cpu, 4)) < 0.03     # same logic, libm vs CUDA math ulps
+    s = scene.stats()
+    with pytest.raises(wrt.WrtError):                                      # square films only, like the reference
+        scene.render_bdpt(cam, wrt.BdptParams(res, res // 2, 1, 0, 10, 3, 4, 0, 1, 0.0, 0))

@@ -61,3 +61,46 @@ def test_empty_and_ragged_inputs(wrt):
     p2, t2 = port.intersect(rays)
     assert np.array_equal(prim, p2) and np.array_equal(util.bits(t), util.bits(t2))
     assert prim[0] == -1 and prim[2] >= 0
+
+
+def _block_mean(img, b):
+    h, w, c = img.shape
+    return img[: h // b * b, : w // b * b].reshape(h // b, b, w // b, b, c).mean(axis=(1, 3))
+
+
+@pytest.mark.parametrize("kind", ["pt", "bdpt"])
+def test_hostsim_integrators_match_reference_statistically(wrt, have_ref, kind):
+    """T3 on the CPU: the kernels' per-path logic (hostsim) against the reference renderer on a small
+    closed Cornell box.  Monte-Carlo estimators with different RNGs: the mean radiance must agree to
+    1.5 % and the 8x8-block rRMSE must be at the reference's own two-seed noise floor."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from hostsim_py import HostSim
+    res = 40
+    sc = scenes.cornell_box_scene(res, res)
+    hs = util.host_scene(wrt, sc); sim = HostSim(hs.desc(), hs); cam = hs.camera()
+    if kind == "pt":
+        spp = 64
+        mine, rays = sim.render_pt(cam, wrt.PtParams(res, res, spp, 5, 11, 0, 1, 0.0))
+        ref = util.ref_scene(sc, "pt")
+        ref.reset_traverse_calls()
+        r1 = ref.render_pt(spp, 5, seed=5489); calls = ref.traverse_calls(); r2 = ref.render_pt(spp, 5, seed=31)
+        n_samples = res * res * spp
+    else:
+        iters = 48
+        mine, rays = sim.render_bdpt(cam, wrt.BdptParams(res, res, iters, 0, 10, 3, 11, 0, 1, 0.0, 0))
+        ref = util.ref_scene(sc, "bdpt")
+        ref.reset_traverse_calls()
+        r1 = ref.render_bdpt(iters, seed=5489) / iters; calls = ref.traverse_calls()
+        r2 = ref.render_bdpt(iters, seed=31) / iters
+        n_samples = res * res * iters
+    rm = (r1 + r2) * 0.5
+    floor = util.rel_rmse(_block_mean(r1, 8), _block_mean(r2, 8))
+    err = util.rel_rmse(_block_mean(mine, 8), _block_mean(rm, 8))
+    print("%s: mean %.5f vs %.5f, rRMSE %.4f floor %.4f, rays/sample %.2f vs %.2f"
+          % (kind, mine.mean(), rm.mean(), err, floor, rays / n_samples, calls / n_samples))
+    assert abs(mine.mean() - rm.mean()) <= 0.015 * rm.mean()
+    assert err <= 1.3 * floor + 0.002
+    # PT queues only the shadow rays that can contribute, BDPT skips the BSDF-sampled DI ray when the light
+    # sample is occluded: never more rays than the reference, and not fewer than 70 % of them
+    assert 0.7 * calls <= rays <= 1.001 * calls

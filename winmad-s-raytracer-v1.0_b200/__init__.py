@@ -492,3 +492,32 @@ class BidirPathTracing(SurfaceIntegrator):
 
     def outputImage(self, filename):
         film_write(filename, np.ascontiguousarray(self.film.transpose(1, 0, 2)), 1.0, 2.2)
+
+
+# ---- multi-GPU: one process per GPU, samples sharded, one sum-reduce of the float film --------------
+def shard_pt(params, rank, world):
+    """Rank `rank` of `world` renders samples k = rank, rank+world, ... of the SAME stratification grid and
+    RNG keys (keyed on pixel and global sample index), pre-scaled by 1/spp: the rank films sum to the
+    1-GPU image."""
+    return PtParams(params.width, params.height, params.spp, params.max_depth, params.seed,
+                    params.sample_first + rank * max(params.sample_stride, 1),
+                    max(params.sample_stride, 1) * world,
+                    params.film_scale if params.film_scale != 0.0 else 1.0 / params.spp)
+
+
+def shard_bdpt(params, rank, world):
+    """Rank `rank` runs iterations it = rank, rank+world, ... (camera path p only ever reads light path p,
+    bidirPathTracing.cpp:222-229, so iterations are independent)."""
+    return BdptParams(params.width, params.height, params.iterations, params.min_path_length,
+                      params.max_path_length, params.control_length, params.seed,
+                      params.iter_first + rank * max(params.iter_stride, 1), max(params.iter_stride, 1) * world,
+                      params.film_scale if params.film_scale != 0.0 else 1.0 / params.iterations,
+                      params.transpose_output)
+
+
+def reduce_film(film_tensor, dst=0):
+    """Sum the per-rank float films onto rank `dst` (NCCL over NVLink on GPUs, gloo on CPU tensors)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(film_tensor, dst, op=dist.ReduceOp.SUM)
+    return film_tensor

@@ -1,8 +1,418 @@
-// placeholder until the BDPT wavefront lands (next commit)
+// Wavefront bidirectional path tracer: wrt_render_bdpt, a drop-in for BidirPathTracing::render
+// (R/src/surfaceIntegrator/bidirPathTracing.cpp:23-265).  Per iteration:
+//   phase A  W*H light sub-paths: extend -> light_shade (store <= maxPathLength-1 vertices per path,
+//            queue the connect-to-camera ray, scatter) -> connection kernel (occlusion + film splat)
+//   phase B  W*H camera sub-paths: extend -> camera_shade (emitter hit, direct-illumination entry,
+//            one connection query per stored light vertex of THIS pixel's light path, scatter)
+//            -> connection kernel -> direct-illumination kernel (shadow ray, then the BSDF-sampled ray)
+// Light vertices live in HBM as 4 x float4 (64 B) per vertex, [vertex k][path] so a warp's accesses
+// to vertex k of consecutive paths are coalesced.  Per-vertex logic is bdpt_logic.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <string>
-#include "wavefront.h"
-namespace wrt { void bdpt_destroy(wrt_wavefront*) {} }
-extern "C" {
-int wrt_render_bdpt(wrt_scene*, const wrt_camera*, const wrt_bdpt_params*, float*) { wrt::set_error("wrt_render_bdpt: not built yet"); return WRT_ERR_INVALID; }
-int wrt_render_bdpt_dev(wrt_scene*, const wrt_camera*, const wrt_bdpt_params*, float*, void*) { wrt::set_error("wrt_render_bdpt: not built yet"); return WRT_ERR_INVALID; }
+#include "bdpt_logic.cuh"
+#include "wavefront_kernels.cuh"
+
+namespace wrt {
+
+void fill_camera(const wrt_camera* c, DevCamera& d);
+
+struct BdptBuffers {
+    unsigned n_paths; int maxv;
+    float* dvc;              // [n_paths] dVC of the live path
+    float4* verts;           // [maxv][n_paths][4]
+    int* nverts;             // [n_paths]
+    ShadowQueue conn; size_t conn_cap;
+    float4* di; size_t di_cap;   // 6 float4 per entry
+};
+
+__device__ __forceinline__ void bdpt_store(const PathPool& pool, float* dvc, uint32_t slot, const RayIn& r, const BdptPath& st)
+{
+    float4* p = reinterpret_cast<float4*>(pool.ray + slot);
+    p[0] = make_float4(r.ox, r.oy, r.oz, r.dx);
+    p[1] = make_float4(r.dy, r.dz, r.tmin, r.tmax);
+    pool.weight_pdf[slot] = make_float4(st.throughput.x, st.throughput.y, st.throughput.z, st.dVCM);
+    pool.meta[slot] = make_uint4(st.index, st.rng.key, st.rng.ctr, (uint32_t)st.length | ((uint32_t)st.spec << 16));
+    dvc[slot] = st.dVC;
 }
+
+__device__ __forceinline__ void bdpt_load(const PathPool& pool, const float* dvc, uint32_t slot, BdptPath& st)
+{
+    const float4 w = pool.weight_pdf[slot];
+    const uint4 m = pool.meta[slot];
+    st.throughput = v3(w.x, w.y, w.z); st.dVCM = w.w; st.dVC = dvc[slot];
+    st.index = m.x; st.rng.key = m.y; st.rng.ctr = m.z;
+    st.length = (int)(m.w & 0xffffu); st.spec = (int)(m.w >> 16);
+}
+
+__device__ __forceinline__ void conn_store(const ShadowQueue& q, size_t pos, const Connection& c)
+{
+    q.a[pos] = make_float4(c.q[0], c.q[1], c.q[2], c.c.x);
+    q.b[pos] = make_float4(c.q[3], c.q[4], c.q[5], c.c.y);
+    q.c[pos] = make_float4(c.q[6], c.q[7], c.q[8], c.c.z);
+    q.pixel[pos] = c.pixel;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_bdpt_light_init(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B, uint32_t* queue)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_paths; i += gridDim.x * blockDim.x) {
+        RayIn r; BdptPath st;
+        bdpt_light_generate(sc, P, i, r, st);
+        bdpt_store(pool, B.dvc, i, r, st);
+        B.nverts[i] = 0;
+        queue[i] = i;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_bdpt_camera_init(BdptParams P, DevCamera cam, PathPool pool, BdptBuffers B, uint32_t* queue)
+{
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_paths; i += gridDim.x * blockDim.x) {
+        RayIn r; BdptPath st;
+        bdpt_camera_generate(P, cam, i, r, st);
+        bdpt_store(pool, B.dvc, i, r, st);
+        queue[i] = i;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_bdpt_light_shade(DevSceneView sc, BdptParams P, DevCamera cam, PathPool pool, BdptBuffers B,
+                   const uint32_t* __restrict__ queue_in, size_t n, uint32_t* __restrict__ queue_out,
+                   unsigned long long* counters)
+{
+    size_t base;
+    while (next_chunk(&counters[WF_WORK2], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        const bool valid = e < n;
+        uint32_t slot = 0;
+        RayIn r; BdptPath st; LightStepOut out;
+        out.alive = false; out.store = false; out.connect = false;
+        if (valid) {
+            slot = queue_in[e];
+            r = pool_load_ray(pool, slot);
+            bdpt_load(pool, B.dvc, slot, st);
+            bdpt_light_step(sc, P, cam, r, st, pool.hit_prim[slot], pool.hit_t[slot], out);
+            if (out.store) {
+                const int k = B.nverts[slot];
+                if (k < B.maxv) {
+                    float4* v = B.verts + ((size_t)k * B.n_paths + slot) * 4;
+                    v[0] = make_float4(out.v.pos.x, out.v.pos.y, out.v.pos.z, out.v.dVCM);
+                    v[1] = make_float4(out.v.throughput.x, out.v.throughput.y, out.v.throughput.z, out.v.dVC);
+                    v[2] = make_float4(out.v.wi.x, out.v.wi.y, out.v.wi.z, __int_as_float(out.v.matid));
+                    v[3] = make_float4(out.v.n.x, out.v.n.y, out.v.n.z, __int_as_float(out.v.length | (out.v.spec << 16)));
+                    B.nverts[slot] = k + 1;
+                }
+            }
+        }
+        const unsigned long long cpos = warp_append(&counters[WF_SHADOW_COUNT], valid && out.connect);
+        if (valid && out.connect) conn_store(B.conn, cpos, out.conn);
+        const bool alive = valid && out.alive;
+        const unsigned long long qpos = warp_append(&counters[WF_NEXT_COUNT], alive);
+        if (alive) { bdpt_store(pool, B.dvc, slot, r, st); queue_out[qpos] = slot; }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_bdpt_camera_shade(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B, const uint32_t* __restrict__ queue_in,
+                    size_t n, uint32_t* __restrict__ queue_out, float* __restrict__ film, unsigned long long* counters)
+{
+    size_t base;
+    while (next_chunk(&counters[WF_WORK2], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        const bool valid = e < n;
+        uint32_t slot = 0;
+        RayIn r; BdptPath st; Bsdf bsdf; V3 hit = v3(0, 0, 0), emit_c = v3(0, 0, 0);
+        bool emit = false, has_di = false; DiEntry di;
+        int k = 0;
+        if (valid) {
+            slot = queue_in[e];
+            r = pool_load_ray(pool, slot);
+            bdpt_load(pool, B.dvc, slot, st);
+            k = bdpt_camera_pre(sc, P, r, st, pool.hit_prim[slot], pool.hit_t[slot], hit, bsdf, emit, emit_c, has_di, di);
+            if (emit) film_add(film, st.index, emit_c, P.film_scale);
+        }
+        const unsigned long long dpos = warp_append(&counters[WF_AUX_COUNT], valid && has_di);
+        if (valid && has_di) {
+            float4* d = B.di + 6 * dpos;
+            d[0] = make_float4(di.q[0], di.q[1], di.q[2], di.cA.x);
+            d[1] = make_float4(di.q[3], di.q[4], di.q[5], di.cA.y);
+            d[2] = make_float4(di.q[6], di.q[7], di.q[8], di.cA.z);
+            d[3] = make_float4(di.bo[0], di.bo[1], di.bo[2], di.cB.x);
+            d[4] = make_float4(di.bd[0], di.bd[1], di.bd[2], di.cB.y);
+            d[5] = make_float4(__int_as_float(di.has_B), __int_as_float(di.light_id), __uint_as_float(di.pixel), di.cB.z);
+        }
+        // connections to the stored vertices of this pixel's light path (warp-uniform trip count)
+        const int nv = (valid && k == 1) ? B.nverts[slot] : 0;
+        int nv_max = nv;
+        for (int o = 16; o > 0; o >>= 1) nv_max = max(nv_max, __shfl_xor_sync(0xffffffffu, nv_max, o));
+        bool stop = false;
+        for (int v = 0; v < nv_max; v++) {
+            bool has = false; Connection c;
+            if (v < nv && !stop) {
+                const float4* q = B.verts + ((size_t)v * B.n_paths + slot) * 4;
+                const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+                LightVertex lv;
+                lv.pos = v3(q0.x, q0.y, q0.z); lv.dVCM = q0.w; lv.throughput = v3(q1.x, q1.y, q1.z); lv.dVC = q1.w;
+                lv.wi = v3(q2.x, q2.y, q2.z); lv.matid = __float_as_int(q2.w); lv.n = v3(q3.x, q3.y, q3.z);
+                const int ls = __float_as_int(q3.w); lv.length = ls & 0xffff; lv.spec = ls >> 16;
+                if (lv.length + 1 + st.length > P.max_len) stop = true;                 // `break` :238-240
+                else if (lv.length + 1 + st.length >= P.min_len) has = bdpt_connect_vertices(sc, P, lv, bsdf, hit, st, c);
+            }
+            const unsigned long long cpos = warp_append(&counters[WF_SHADOW_COUNT], has);
+            if (has) conn_store(B.conn, cpos, c);
+        }
+        bool alive = false;
+        if (valid && k != 0) {
+            alive = bdpt_sample_scattering(sc, bsdf, hit, r, st);
+            if (alive) st.length += 1;
+        }
+        const unsigned long long qpos = warp_append(&counters[WF_NEXT_COUNT], alive);
+        if (alive) { bdpt_store(pool, B.dvc, slot, r, st); queue_out[qpos] = slot; }
+    }
+}
+
+// getDirectIllumination's two scene queries: the light-sample shadow ray, then (only if that sample
+// is visible, otherwise the outer weight is 0) the BSDF-sampled closest-hit ray.
+template <bool PRUNED>
+__global__ void __launch_bounds__(kBlock)
+k_bdpt_di(DevSceneView sc, const float4* __restrict__ di, float* __restrict__ film, float scale, unsigned long long* counters)
+{
+    const size_t n = (size_t)counters[WF_AUX_COUNT];
+    size_t base;
+    unsigned long long extra = 0;
+    while (next_chunk(&counters[WF_WORK4], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        if (e >= n) continue;
+        const float4* d = di + 6 * e;
+        const float4 d0 = d[0], d1 = d[1], d2 = d[2];
+        RayIn r;
+        make_ray(d0.x, d0.y, d0.z, d1.x, d1.y, d1.z, r);
+        if (!shadow_visible<PRUNED>(sc, r, d2.x, d2.y, d2.z)) continue;
+        const float4 d5 = d[5];
+        const uint32_t pixel = __float_as_uint(d5.z);
+        film_add(film, pixel, v3(d0.w, d1.w, d2.w), scale);
+        if (__float_as_int(d5.x)) {
+            const float4 d3 = d[3], d4 = d[4];
+            make_ray(d3.x, d3.y, d3.z, d4.x, d4.y, d4.z, r);
+            float t;
+            const int prim = kd_traverse<PRUNED, false>(sc, r, t, nullptr);
+            extra++;
+            if (prim >= 0) {
+                const int m = __float_as_int(__ldg(&sc.prims[3 * (size_t)prim]).w);
+                if (m < 0 && -m - 1 == __float_as_int(d5.y)) film_add(film, pixel, v3(d3.w, d4.w, d5.w), scale);
+            }
+        }
+    }
+    if (extra) atomicAdd(&counters[WF_AUX2_COUNT], extra);
+}
+
+__global__ void k_transpose_film(const float* __restrict__ in, float* __restrict__ out, int n)
+{
+    const int i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && j < n)
+        for (int c = 0; c < 3; c++) out[3 * ((size_t)j * n + i) + c] = in[3 * ((size_t)i * n + j) + c];
+}
+
+void bdpt_destroy(wrt_wavefront* wf)
+{
+    BdptBuffers* B = (BdptBuffers*)wf->bdpt;
+    if (!B) return;
+    cudaFree(B->dvc); cudaFree(B->verts); cudaFree(B->nverts);
+    cudaFree(B->conn.a); cudaFree(B->conn.b); cudaFree(B->conn.c); cudaFree(B->conn.pixel); cudaFree(B->di);
+    delete B;
+    wf->bdpt = nullptr;
+}
+
+static int bdpt_buffers(wrt_wavefront* wf, unsigned n_paths, int maxv, BdptBuffers** out)
+{
+    BdptBuffers* B = (BdptBuffers*)wf->bdpt;
+    if (B && B->n_paths >= n_paths && B->maxv >= maxv) {
+        // the vertex array is indexed [k][n_paths]: keep the allocation's own stride
+        *out = B; return WRT_OK;
+    }
+    bdpt_destroy(wf);
+    B = new BdptBuffers();
+    memset(B, 0, sizeof *B);
+    wf->bdpt = B;
+    B->n_paths = n_paths; B->maxv = maxv;
+    B->conn_cap = (size_t)n_paths * (size_t)(maxv + 1);
+    B->di_cap = n_paths;
+    WRT_CUDA(cudaMalloc((void**)&B->dvc, (size_t)n_paths * sizeof(float)));
+    WRT_CUDA(cudaMalloc((void**)&B->verts, (size_t)n_paths * maxv * 4 * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->nverts, (size_t)n_paths * sizeof(int)));
+    WRT_CUDA(cudaMalloc((void**)&B->conn.a, B->conn_cap * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->conn.b, B->conn_cap * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->conn.c, B->conn_cap * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->conn.pixel, B->conn_cap * sizeof(uint32_t)));
+    WRT_CUDA(cudaMalloc((void**)&B->di, B->di_cap * 6 * sizeof(float4)));
+    *out = B;
+    return WRT_OK;
+}
+
+static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* d_film, cudaStream_t st)
+{
+    if (!cam || !p || p->width <= 0 || p->height <= 0 || p->iterations <= 0 || p->max_path_length < 1) {
+        set_error("wrt_render_bdpt: bad parameters"); return WRT_ERR_INVALID;
+    }
+    if (p->width != p->height) {
+        set_error("wrt_render_bdpt: the film must be square (the reference transposes it in place, bidirPathTracing.cpp:29-45)");
+        return WRT_ERR_INVALID;
+    }
+    if (sc->view.n_lights <= 0) { set_error("wrt_render_bdpt: the scene has no light"); return WRT_ERR_INVALID; }
+    if ((long long)p->width * p->height > (1ll << 26)) { set_error("wrt_render_bdpt: film too large"); return WRT_ERR_INVALID; }
+    BdptParams P;
+    P.width = p->width; P.height = p->height; P.min_len = p->min_path_length; P.max_len = p->max_path_length;
+    P.control_len = p->control_length; P.seed = p->seed; P.iteration = 0;
+    P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->iterations;
+    P.n_paths = (unsigned)(p->width * p->height);
+    P.light_path_num = (float)(p->width * p->height);
+    { const char* e = getenv("WRT_BDPT_SKIP_GATED"); P.trace_gated = (e && atoi(e)) ? 0 : 1; }
+    const int stride = p->iter_stride > 0 ? p->iter_stride : 1;
+    if (p->iter_first < 0 || p->iter_first >= p->iterations) { set_error("wrt_render_bdpt: iter_first out of range"); return WRT_ERR_INVALID; }
+    const int maxv = std::max(P.max_len - 1, 1);
+    DevCamera dc; fill_camera(cam, dc);
+
+    wrt_wavefront* wf = nullptr;
+    int rc = wavefront_get(sc, (int)std::max(P.n_paths, 1024u), &wf);
+    if (rc) return rc;
+    BdptBuffers* B = nullptr;
+    rc = bdpt_buffers(wf, P.n_paths, maxv, &B);
+    if (rc) return rc;
+    BdptBuffers Bv = *B;
+    Bv.n_paths = B->n_paths;      // stride of the vertex array
+    const bool pruned = sc->traversal_mode == WRT_TRAVERSE_PRUNED;
+    const bool counting = sc->counting != 0;
+
+    static int g_li = persistent_grid_for((const void*)k_bdpt_light_init, kBlock);
+    static int g_ci = persistent_grid_for((const void*)k_bdpt_camera_init, kBlock);
+    static int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
+    static int g_ext_e = persistent_grid_for((const void*)k_pt_extend<false>, kBlock);
+    static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count, kBlock);
+    static int g_ls = persistent_grid_for((const void*)k_bdpt_light_shade, kBlock);
+    static int g_cs = persistent_grid_for((const void*)k_bdpt_camera_shade, kBlock);
+    static int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
+    static int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
+    static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count, kBlock);
+    static int g_di_p = persistent_grid_for((const void*)k_bdpt_di<true>, kBlock);
+    static int g_di_e = persistent_grid_for((const void*)k_bdpt_di<false>, kBlock);
+
+    rc = wavefront_events(wf, 4 * 64);
+    if (rc) return rc;
+    const int kMaxTimed = 4096;
+    int timed = 0;
+    sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
+    WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
+
+    for (int it = p->iter_first; it < p->iterations; it += stride) {
+        P.iteration = it;
+        for (int phase = 0; phase < 2; phase++) {
+            if (phase == 0) k_bdpt_light_init<<<g_li, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[0]);
+            else k_bdpt_camera_init<<<g_ci, kBlock, 0, st>>>(P, dc, wf->pool, Bv, wf->queue[0]);
+            WRT_CUDA(cudaGetLastError());
+            sc->stats.kernel_launches += 1;
+            size_t n = P.n_paths;
+            int cur = 0;
+            while (n > 0) {
+                const bool time_it = timed < kMaxTimed;
+                if (time_it && 4 * (timed + 1) > wf->n_ev) { rc = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (rc) return rc; }
+                cudaEvent_t* ev = time_it ? &wf->ev[4 * timed] : nullptr;
+                WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), st));
+                if (ev) cudaEventRecord(ev[0], st);
+                if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+                if (ev) cudaEventRecord(ev[1], st);
+                if (phase == 0)
+                    k_bdpt_light_shade<<<g_ls, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, Bv, wf->queue[cur], n, wf->queue[cur ^ 1], wf->counters);
+                else
+                    k_bdpt_camera_shade<<<g_cs, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[cur], n, wf->queue[cur ^ 1], d_film, wf->counters);
+                if (ev) cudaEventRecord(ev[2], st);
+                if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
+                else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
+                else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
+                if (phase == 1) {
+                    if (pruned) k_bdpt_di<true><<<g_di_p, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters);
+                    else k_bdpt_di<false><<<g_di_e, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters);
+                }
+                if (ev) { cudaEventRecord(ev[3], st); timed++; }
+                WRT_CUDA(cudaGetLastError());
+                WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters, WF_PER_ITER * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                WRT_CUDA(cudaStreamSynchronize(st));
+                sc->stats.closest_rays += n + wf->h_counters[WF_AUX2_COUNT];
+                sc->stats.extend_launches += 1; sc->stats.extend_rays += n;
+                sc->stats.shadow_rays += wf->h_counters[WF_SHADOW_COUNT] + wf->h_counters[WF_AUX_COUNT];
+                sc->stats.kernel_launches += 3 + (phase == 1 ? 1 : 0);
+                n = (size_t)wf->h_counters[WF_NEXT_COUNT];
+                cur ^= 1;
+            }
+        }
+        sc->stats.samples += P.n_paths;
+    }
+    wavefront_sum_stage_times(sc, wf, timed);
+    if (counting) {
+        unsigned long long h[4];
+        WRT_CUDA(cudaMemcpyAsync(h, &wf->counters[WF_VISITS], sizeof h, cudaMemcpyDeviceToHost, st));
+        WRT_CUDA(cudaStreamSynchronize(st));
+        sc->stats.inner_visits += h[0]; sc->stats.leaf_visits += h[1]; sc->stats.tri_tests += h[2]; sc->stats.sphere_tests += h[3];
+    }
+    return WRT_OK;
+}
+
+}  // namespace wrt
+
+using namespace wrt;
+
+extern "C" {
+
+int wrt_render_bdpt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* d_film, void* stream)
+{
+    if (!sc || !d_film || !p) { set_error("wrt_render_bdpt_dev: null argument"); return WRT_ERR_INVALID; }
+    WRT_CUDA(cudaSetDevice(sc->device));
+    if (p->transpose_output) { set_error("wrt_render_bdpt_dev: transpose_output is only offered by the host-buffer call"); return WRT_ERR_INVALID; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    int rc = render_bdpt_device(sc, cam, p, d_film, st);
+    if (rc) return rc;
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_render_ms = ms;
+    return WRT_OK;
+}
+
+int wrt_render_bdpt(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* film)
+{
+    if (!sc || !film || !p) { set_error("wrt_render_bdpt: null argument"); return WRT_ERR_INVALID; }
+    WRT_CUDA(cudaSetDevice(sc->device));
+    if (p->width <= 0 || p->height <= 0 || p->width != p->height) {
+        set_error("wrt_render_bdpt: the film must be square and non-empty (bidirPathTracing.cpp:29-45)"); return WRT_ERR_INVALID;
+    }
+    wrt_wavefront* wf = nullptr;
+    int rc = wavefront_get(sc, std::max(p->width * p->height, 1024), &wf);   // grow the pool first (frees the film)
+    if (rc) return rc;
+    const size_t floats = (size_t)p->width * p->height * 3;
+    float* d_film = nullptr;
+    rc = wavefront_film(sc, floats * 2, &d_film);
+    if (rc) return rc;
+    cudaStream_t st = sc->stream;
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    WRT_CUDA(cudaMemsetAsync(d_film, 0, floats * sizeof(float), st));
+    rc = render_bdpt_device(sc, cam, p, d_film, st);
+    if (rc) return rc;
+    float* src = d_film;
+    if (p->transpose_output) {
+        dim3 b(16, 16), g((p->width + 15) / 16, (p->width + 15) / 16);
+        k_transpose_film<<<g, b, 0, st>>>(d_film, d_film + floats, p->width);
+        WRT_CUDA(cudaGetLastError());
+        sc->stats.kernel_launches += 1;
+        src = d_film + floats;
+    }
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaMemcpyAsync(film, src, floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_render_ms = ms;
+    return WRT_OK;
+}
+
+}  // extern "C"

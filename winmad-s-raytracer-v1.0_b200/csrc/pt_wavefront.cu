@@ -18,21 +18,9 @@
 #include <cstdio>
 #include <string>
 #include "pt_logic.cuh"
-#include "wavefront.h"
-#include "warp_utils.cuh"
+#include "wavefront_kernels.cuh"
 
 namespace wrt {
-
-constexpr int kBlock = 128;
-
-__device__ __forceinline__ RayIn pool_load_ray(const PathPool& pool, uint32_t slot)
-{
-    const float4* p = reinterpret_cast<const float4*>(pool.ray + slot);
-    const float4 a = p[0], b = p[1];
-    RayIn r;
-    r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
-    return r;
-}
 
 __device__ __forceinline__ void pool_store(const PathPool& pool, uint32_t slot, const RayIn& r, const PathData& pd)
 {
@@ -52,13 +40,6 @@ __device__ __forceinline__ void pool_load_data(const PathPool& pool, uint32_t sl
     pd.length = (int)(m.w & 0xffffu); pd.last_specular = (int)(m.w >> 16);
 }
 
-__device__ __forceinline__ void film_add(float* film, uint32_t pixel, V3 c, float scale)
-{
-    atomicAdd(&film[3 * (size_t)pixel + 0], c.x * scale);
-    atomicAdd(&film[3 * (size_t)pixel + 1], c.y * scale);
-    atomicAdd(&film[3 * (size_t)pixel + 2], c.z * scale);
-}
-
 __global__ void __launch_bounds__(kBlock)
 k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0)
 {
@@ -68,72 +49,6 @@ k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0
         pool_store(pool, s, r, pd);
         queue[s] = s;
     }
-}
-
-template <bool PRUNED>
-__global__ void __launch_bounds__(kBlock)
-k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters)
-{
-    size_t base;
-    while (next_chunk(&counters[WF_WORK], n, base)) {
-        const size_t e = base + (threadIdx.x & 31);
-        if (e >= n) continue;
-        const uint32_t slot = queue[e];
-        const RayIn r = pool_load_ray(pool, slot);
-        float t;
-        const int prim = kd_traverse<PRUNED, false>(sc, r, t, nullptr);
-        pool.hit_prim[slot] = prim;
-        pool.hit_t[slot] = t;
-    }
-}
-
-// Counting-mode variants: EXACT traversal with the reference-semantics visit counters.
-__global__ void __launch_bounds__(kBlock)
-k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters)
-{
-    size_t base;
-    unsigned long long a = 0, b = 0, c = 0, d = 0;
-    while (next_chunk(&counters[WF_WORK], n, base)) {
-        const size_t e = base + (threadIdx.x & 31);
-        if (e >= n) continue;
-        const uint32_t slot = queue[e];
-        const RayIn r = pool_load_ray(pool, slot);
-        VisitCounters vc = { 0u, 0u, 0u, 0u };
-        float t;
-        const int prim = kd_traverse<false, true>(sc, r, t, &vc);
-        pool.hit_prim[slot] = prim;
-        pool.hit_t[slot] = t;
-        a += vc.inner; b += vc.leaf; c += vc.tri; d += vc.sph;
-    }
-    atomicAdd(&counters[WF_VISITS + 0], a); atomicAdd(&counters[WF_VISITS + 1], b);
-    atomicAdd(&counters[WF_VISITS + 2], c); atomicAdd(&counters[WF_VISITS + 3], d);
-}
-
-__global__ void __launch_bounds__(kBlock)
-k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters)
-{
-    const size_t n = (size_t)counters[WF_SHADOW_COUNT];
-    size_t base;
-    unsigned long long a = 0, b = 0, c = 0, d = 0;
-    while (next_chunk(&counters[WF_WORK3], n, base)) {
-        const size_t e = base + (threadIdx.x & 31);
-        if (e >= n) continue;
-        const float4 qa = sq.a[e], qb = sq.b[e], qc = sq.c[e];
-        RayIn r;
-        make_ray(qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, r);
-        VisitCounters vc = { 0u, 0u, 0u, 0u };
-        float t;
-        const int prim = kd_traverse<false, true>(sc, r, t, &vc);
-        a += vc.inner; b += vc.leaf; c += vc.tri; d += vc.sph;
-        bool vis = prim < 0;
-        if (!vis) {
-            const float ex = (r.ox + r.dx * t) - qc.x, ey = (r.oy + r.dy * t) - qc.y, ez = (r.oz + r.dz * t) - qc.z;
-            vis = !(ex < -WRT_EPS) && !(ex > WRT_EPS) && !(ey < -WRT_EPS) && !(ey > WRT_EPS) && !(ez < -WRT_EPS) && !(ez > WRT_EPS);
-        }
-        if (vis) film_add(film, sq.pixel[e], v3(qa.w, qb.w, qc.w), scale);
-    }
-    atomicAdd(&counters[WF_VISITS + 0], a); atomicAdd(&counters[WF_VISITS + 1], b);
-    atomicAdd(&counters[WF_VISITS + 2], c); atomicAdd(&counters[WF_VISITS + 3], d);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -175,23 +90,6 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
             pool_store(pool, slot, r, pd);
             queue_out[qpos] = slot;
         }
-    }
-}
-
-template <bool PRUNED>
-__global__ void __launch_bounds__(kBlock)
-k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters)
-{
-    const size_t n = (size_t)counters[WF_SHADOW_COUNT];
-    size_t base;
-    while (next_chunk(&counters[WF_WORK3], n, base)) {
-        const size_t e = base + (threadIdx.x & 31);
-        if (e >= n) continue;
-        const float4 a = sq.a[e], b = sq.b[e], c = sq.c[e];
-        RayIn r;
-        make_ray(a.x, a.y, a.z, b.x, b.y, b.z, r);
-        if (shadow_visible<PRUNED>(sc, r, c.x, c.y, c.z))
-            film_add(film, sq.pixel[e], v3(a.w, b.w, c.w), scale);
     }
 }
 

@@ -13,7 +13,9 @@ enum {
     WF_WORK3 = 2,       //                     shadow kernel
     WF_NEXT_COUNT = 3,  // entries appended to the next-bounce queue
     WF_SHADOW_COUNT = 4,
-    WF_AUX_COUNT = 5,
+    WF_AUX_COUNT = 5,   // BDPT direct-illumination entries
+    WF_WORK4 = 6,
+    WF_AUX2_COUNT = 7,  // BDPT: BSDF-sampled rays traced by the DI kernel
     WF_PER_ITER = 8,    // counters [0, WF_PER_ITER) are zeroed before every iteration
     WF_NEXT_SAMPLE = 8, // next camera sample to hand out (path regeneration)
     WF_LIGHT_VERTS = 9,
