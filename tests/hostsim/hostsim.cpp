@@ -95,6 +95,18 @@ void hs_count_visits(void* hv, const wrt_ray* rays, size_t n, int pruned, unsign
     }
 }
 
+void hs_visits_per_ray(void* hv, const wrt_ray* rays, size_t n, int pruned, unsigned* leaf, unsigned* tri)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    for (size_t i = 0; i < n; i++) {
+        RayIn r = { rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz, rays[i].tmin, rays[i].tmax };
+        VisitCounters vc = { 0, 0, 0, 0 };
+        float tt;
+        if (pruned) kd_traverse<true, true>(sc, r, tt, &vc); else kd_traverse<false, true>(sc, r, tt, &vc);
+        leaf[i] = vc.leaf; tri[i] = vc.tri + vc.sph;
+    }
+}
+
 // Sequential driver of the same pt_generate / pt_shade the CUDA kernels call.
 // rays_out (optional): closest + shadow rays traced.
 void hs_render_pt(void* hv, const wrt_camera* cam, const wrt_pt_params* p, int pruned, float* film,

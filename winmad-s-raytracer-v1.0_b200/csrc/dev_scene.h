@@ -70,8 +70,9 @@ struct wrt_scene {
     void* d_scratch_out; size_t scratch_out_bytes;
     unsigned long long* d_counters;  // small device counter block
     cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
-    struct wrt_wavefront* wf;        // lazily created integrator state
+    cudaEvent_t ev0, ev1, ev_fork;
+    struct wrt_wavefront* wf;        // lazily created integrator state (sub-pool 0; owns the film and BDPT buffers)
+    struct wrt_wavefront* wf_extra[7]; // further PT sub-pools (each with its own stream), see pt_wavefront.cu
 };
 
 namespace wrt {

@@ -41,11 +41,11 @@ __device__ __forceinline__ void pool_load_data(const PathPool& pool, uint32_t sl
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0)
+k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0, unsigned long long first_sample)
 {
     for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n0; s += gridDim.x * blockDim.x) {
         RayIn r; PathData pd;
-        pt_generate(P, cam, s, r, pd);
+        pt_generate(P, cam, first_sample + s, r, pd);
         pool_store(pool, s, r, pd);
         queue[s] = s;
     }
@@ -53,7 +53,8 @@ k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0
 
 __global__ void __launch_bounds__(kBlock)
 k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in, size_t n,
-           uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* counters)
+           uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* counters,
+           unsigned long long* next_sample)
 {
     size_t base;
     while (next_chunk(&counters[WF_WORK2], n, base)) {
@@ -80,7 +81,7 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
         // path regeneration: a finished path's slot takes the next camera sample
         bool alive = valid && out.alive;
         const bool dead = valid && !out.alive;
-        const unsigned long long snew = warp_append(&counters[WF_NEXT_SAMPLE], dead);
+        const unsigned long long snew = warp_append(next_sample, dead);
         if (dead && snew < P.total_samples) {
             pt_generate(P, cam, snew, r, pd);
             alive = true;
@@ -94,14 +95,17 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
 }
 
 // ---- wavefront state -------------------------------------------------------------------------------
-int wavefront_get(wrt_scene* sc, int capacity, wrt_wavefront** out)
+static void wavefront_free(wrt_wavefront* wf);
+
+int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** out)
 {
-    if (sc->wf && sc->wf->capacity >= capacity) { *out = sc->wf; return WRT_OK; }
-    wavefront_destroy(sc);
+    wrt_wavefront** where = slot == 0 ? &sc->wf : &sc->wf_extra[slot - 1];
+    if (*where && (*where)->capacity >= capacity) { *out = *where; return WRT_OK; }
+    if (*where) { wavefront_free(*where); *where = nullptr; }
     wrt_wavefront* wf = new wrt_wavefront();
     memset(wf, 0, sizeof *wf);
     wf->capacity = capacity;
-    sc->wf = wf;
+    *where = wf;
     const size_t P = (size_t)capacity;
     WRT_CUDA(cudaMalloc((void**)&wf->pool.ray, P * sizeof(wrt_ray)));
     WRT_CUDA(cudaMalloc((void**)&wf->pool.weight_pdf, P * sizeof(float4)));
@@ -116,9 +120,13 @@ int wavefront_get(wrt_scene* sc, int capacity, wrt_wavefront** out)
     WRT_CUDA(cudaMalloc((void**)&wf->shadow.pixel, P * sizeof(uint32_t)));
     WRT_CUDA(cudaMalloc((void**)&wf->counters, WF_COUNTERS * sizeof(unsigned long long)));
     WRT_CUDA(cudaMallocHost((void**)&wf->h_counters, WF_COUNTERS * sizeof(unsigned long long)));
+    WRT_CUDA(cudaStreamCreateWithFlags(&wf->stream, cudaStreamNonBlocking));
+    WRT_CUDA(cudaEventCreateWithFlags(&wf->join_ev, cudaEventDisableTiming));
     *out = wf;
     return WRT_OK;
 }
+
+int wavefront_get(wrt_scene* sc, int capacity, wrt_wavefront** out) { return wavefront_get_slot(sc, 0, capacity, out); }
 
 int wavefront_film(wrt_scene* sc, size_t floats, float** out)
 {
@@ -160,9 +168,8 @@ void wavefront_sum_stage_times(wrt_scene* sc, wrt_wavefront* wf, int iters_timed
     sc->stats.extend_ms = ext; sc->stats.shade_ms = shd; sc->stats.shadow_ms = shw;
 }
 
-void wavefront_destroy(wrt_scene* sc)
+static void wavefront_free(wrt_wavefront* wf)
 {
-    wrt_wavefront* wf = sc->wf;
     if (!wf) return;
     bdpt_destroy(wf);
     cudaFree(wf->pool.ray); cudaFree(wf->pool.weight_pdf); cudaFree(wf->pool.meta);
@@ -172,8 +179,16 @@ void wavefront_destroy(wrt_scene* sc)
     cudaFree(wf->counters); cudaFreeHost(wf->h_counters); cudaFree(wf->film);
     for (int i = 0; i < wf->n_ev; i++) cudaEventDestroy(wf->ev[i]);
     delete[] wf->ev;
+    if (wf->stream) cudaStreamDestroy(wf->stream);
+    if (wf->join_ev) cudaEventDestroy(wf->join_ev);
     delete wf;
+}
+
+void wavefront_destroy(wrt_scene* sc)
+{
+    wavefront_free(sc->wf);
     sc->wf = nullptr;
+    for (int i = 0; i < 7; i++) { wavefront_free(sc->wf_extra[i]); sc->wf_extra[i] = nullptr; }
 }
 
 void fill_camera(const wrt_camera* c, DevCamera& d)
@@ -187,7 +202,7 @@ void fill_camera(const wrt_camera* c, DevCamera& d)
 static int pool_capacity()
 {
     const char* e = getenv("WRT_POOL_PATHS");
-    long v = e ? atol(e) : (1L << 21);
+    long v = e ? atol(e) : (1L << 23);
     if (v < 1024) v = 1024;
     if (v > (1L << 26)) v = 1L << 26;
     return (int)v;
@@ -209,11 +224,32 @@ static int pt_fill_params(const wrt_pt_params* p, PtParams& P)
     return WRT_OK;
 }
 
-static int pt_capacity(const PtParams& P)
+static int sub_pools()
 {
-    const unsigned long long cap = std::min<unsigned long long>((unsigned long long)pool_capacity(), P.total_samples);
-    return (int)std::max<unsigned long long>(cap, 1024ull);
+    const char* e = getenv("WRT_SUBPOOLS");
+    int k = e ? atoi(e) : 2;
+    return std::min(std::max(k, 1), 8);
 }
+
+// How the pool is split: K sub-pools, each with its own queues, counters and stream.  The kernels of
+// different sub-pools overlap on the GPU, so the tail of one sub-pool's extend launch (a handful of very
+// long rays, ~3.5 ms on the 1 M-triangle scene) is covered by the bulk of another's.
+struct PtPlan { int k; int cap[8]; };
+
+static void pt_plan(const PtParams& P, PtPlan& plan)
+{
+    unsigned long long total = std::min<unsigned long long>((unsigned long long)pool_capacity(), P.total_samples);
+    total = std::max<unsigned long long>(total, 1024ull);
+    int k = sub_pools();
+    if (total < (1ull << 18)) k = 1;
+    plan.k = k;
+    const unsigned long long per = (total + k - 1) / k;
+    for (int j = 0; j < k; j++) plan.cap[j] = (int)std::max<unsigned long long>(per, 1024ull);
+}
+
+struct SubState {
+    wrt_wavefront* wf; size_t n; int cur; bool in_flight; int timed;
+};
 
 static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st)
 {
@@ -223,12 +259,16 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     int rc = pt_fill_params(p, P);
     if (rc) return rc;
     DevCamera dc; fill_camera(cam, dc);
-    wrt_wavefront* wf = nullptr;
-    rc = wavefront_get(sc, pt_capacity(P), &wf);
-    if (rc) return rc;
-    const unsigned long long cap = std::min<unsigned long long>((unsigned long long)wf->capacity, P.total_samples);
-    const unsigned n0 = (unsigned)cap;
+    PtPlan plan; pt_plan(P, plan);
+    SubState sub[8];
+    for (int j = 0; j < plan.k; j++) {
+        rc = wavefront_get_slot(sc, j, plan.cap[j], &sub[j].wf);
+        if (rc) return rc;
+        rc = wavefront_events(sub[j].wf, 4 * 64);
+        if (rc) return rc;
+    }
     const bool pruned = sc->traversal_mode == WRT_TRAVERSE_PRUNED;
+    const bool counting = sc->counting != 0;
 
     static int g_init = persistent_grid_for((const void*)k_pt_init, kBlock);
     static int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
@@ -236,60 +276,101 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     static int g_shade = persistent_grid_for((const void*)k_pt_shade, kBlock);
     static int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
     static int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
-
-    WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
-    k_pt_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0);
-    WRT_CUDA(cudaGetLastError());
-    {
-        unsigned long long first = n0;
-        WRT_CUDA(cudaMemcpyAsync(&wf->counters[WF_NEXT_SAMPLE], &first, sizeof first, cudaMemcpyHostToDevice, st));
-    }
-    sc->stats.kernel_launches += 1;
-    size_t n = n0;
-    int cur = 0;
-    unsigned long long iters = 0;
-    const int kMaxTimed = 4096;
-    rc = wavefront_events(wf, 4 * 64);
-    if (rc) return rc;
-    int timed = 0;
-    const bool counting = sc->counting != 0;
     static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count, kBlock);
     static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count, kBlock);
-    sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
-    while (n > 0) {
-        const bool time_it = timed < kMaxTimed;
-        if (time_it && 4 * (timed + 1) > wf->n_ev) { rc = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (rc) return rc; }
-        cudaEvent_t* ev = time_it ? &wf->ev[4 * timed] : nullptr;
-        WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), st));
-        if (ev) cudaEventRecord(ev[0], st);
-        if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-        else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-        if (ev) cudaEventRecord(ev[1], st);
-        k_pt_shade<<<g_shade, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
-                                               d_film, wf->counters);
-        if (ev) cudaEventRecord(ev[2], st);
-        if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
-        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
-        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
-        if (ev) { cudaEventRecord(ev[3], st); timed++; }
+
+    // initial fill: sub-pool j starts with samples [first, first + n0_j)
+    unsigned long long first = 0;
+    for (int j = 0; j < plan.k; j++) {
+        wrt_wavefront* wf = sub[j].wf;
+        const unsigned long long left = P.total_samples - first;
+        const unsigned n0 = (unsigned)std::min<unsigned long long>((unsigned long long)plan.cap[j], left);
+        WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
+        if (n0) k_pt_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first);
         WRT_CUDA(cudaGetLastError());
-        WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters, WF_PER_ITER * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        WRT_CUDA(cudaStreamSynchronize(st));
-        sc->stats.closest_rays += n;
-        sc->stats.extend_launches += 1; sc->stats.extend_rays += n;
+        sub[j].n = n0; sub[j].cur = 0; sub[j].in_flight = false; sub[j].timed = 0;
+        first += n0;
+        sc->stats.kernel_launches += n0 ? 1 : 0;
+    }
+    unsigned long long* next_sample = &sub[0].wf->counters[WF_NEXT_SAMPLE];
+    WRT_CUDA(cudaMemcpyAsync(next_sample, &first, sizeof first, cudaMemcpyHostToDevice, st));
+    // fork: the sub-pool streams start after everything queued on the caller's stream so far
+    WRT_CUDA(cudaEventRecord(sc->ev_fork, st));
+    for (int j = 0; j < plan.k; j++) WRT_CUDA(cudaStreamWaitEvent(sub[j].wf->stream, sc->ev_fork, 0));
+
+    const int kMaxTimed = 2048;
+    sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
+    unsigned long long iters = 0;
+
+    auto launch = [&](SubState& s) -> int {
+        wrt_wavefront* wf = s.wf;
+        cudaStream_t q = wf->stream;
+        const bool time_it = s.timed < kMaxTimed;
+        if (time_it && 4 * (s.timed + 1) > wf->n_ev) { int r = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (r) return r; }
+        cudaEvent_t* ev = time_it ? &wf->ev[4 * s.timed] : nullptr;
+        const size_t n = s.n; const int cur = s.cur;
+        WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), q));
+        if (ev) cudaEventRecord(ev[0], q);
+        if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        if (ev) cudaEventRecord(ev[1], q);
+        k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
+                                              d_film, wf->counters, next_sample);
+        if (ev) cudaEventRecord(ev[2], q);
+        if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        if (ev) { cudaEventRecord(ev[3], q); s.timed++; }
+        WRT_CUDA(cudaGetLastError());
+        WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters, WF_PER_ITER * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q));
+        s.in_flight = true;
+        return WRT_OK;
+    };
+    auto complete = [&](SubState& s) -> int {
+        wrt_wavefront* wf = s.wf;
+        WRT_CUDA(cudaStreamSynchronize(wf->stream));
+        sc->stats.closest_rays += s.n;
+        sc->stats.extend_launches += 1; sc->stats.extend_rays += s.n;
         sc->stats.shadow_rays += wf->h_counters[WF_SHADOW_COUNT];
         sc->stats.kernel_launches += 3;
-        n = (size_t)wf->h_counters[WF_NEXT_COUNT];
-        cur ^= 1;
+        s.n = (size_t)wf->h_counters[WF_NEXT_COUNT];
+        s.cur ^= 1;
+        s.in_flight = false;
+        return WRT_OK;
+    };
+
+    for (int j = 0; j < plan.k; j++) if (sub[j].n > 0) { rc = launch(sub[j]); if (rc) return rc; }
+    for (;;) {
+        bool any = false;
+        for (int j = 0; j < plan.k; j++) {
+            if (!sub[j].in_flight) continue;
+            any = true;
+            rc = complete(sub[j]); if (rc) return rc;
+            if (sub[j].n > 0) { rc = launch(sub[j]); if (rc) return rc; }
+        }
+        if (!any) break;
         if (++iters > (1ull << 32)) { set_error("wrt_render_pt: runaway iteration count"); return WRT_ERR_CUDA; }
     }
-    wavefront_sum_stage_times(sc, wf, timed);
+    // join: the caller's stream continues after every sub-pool stream
+    for (int j = 0; j < plan.k; j++) {
+        WRT_CUDA(cudaEventRecord(sub[j].wf->join_ev, sub[j].wf->stream));
+        WRT_CUDA(cudaStreamWaitEvent(st, sub[j].wf->join_ev, 0));
+    }
+    // stage times: sum of per-launch CUDA-event durations over all sub-pools (launches of different
+    // sub-pools overlap, so the sums can exceed the wall time of the render)
+    double ext = 0, shd = 0, shw = 0;
+    for (int j = 0; j < plan.k; j++) {
+        wavefront_sum_stage_times(sc, sub[j].wf, sub[j].timed);
+        ext += sc->stats.extend_ms; shd += sc->stats.shade_ms; shw += sc->stats.shadow_ms;
+    }
+    sc->stats.extend_ms = ext; sc->stats.shade_ms = shd; sc->stats.shadow_ms = shw;
     if (counting) {
-        unsigned long long h[4];
-        WRT_CUDA(cudaMemcpyAsync(h, &wf->counters[WF_VISITS], sizeof h, cudaMemcpyDeviceToHost, st));
-        WRT_CUDA(cudaStreamSynchronize(st));
-        sc->stats.inner_visits += h[0]; sc->stats.leaf_visits += h[1]; sc->stats.tri_tests += h[2]; sc->stats.sphere_tests += h[3];
+        for (int j = 0; j < plan.k; j++) {
+            unsigned long long h[4];
+            WRT_CUDA(cudaMemcpy(h, &sub[j].wf->counters[WF_VISITS], sizeof h, cudaMemcpyDeviceToHost));
+            sc->stats.inner_visits += h[0]; sc->stats.leaf_visits += h[1]; sc->stats.tri_tests += h[2]; sc->stats.sphere_tests += h[3];
+        }
     }
     sc->stats.samples += P.total_samples;
     return WRT_OK;
@@ -323,8 +404,11 @@ int wrt_render_pt(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, 
     int rc = pt_fill_params(p, P);
     if (rc) return rc;
     wrt_wavefront* wf = nullptr;
-    rc = wavefront_get(sc, pt_capacity(P), &wf);   // grow the pool first: re-creating it frees the film
-    if (rc) return rc;
+    {   // grow sub-pool 0 first: re-creating it frees the film it owns
+        PtPlan plan; pt_plan(P, plan);
+        rc = wavefront_get_slot(sc, 0, plan.cap[0], &wf);
+        if (rc) return rc;
+    }
     const size_t floats = (size_t)p->width * p->height * 3;
     float* d_film = nullptr;
     rc = wavefront_film(sc, floats, &d_film);

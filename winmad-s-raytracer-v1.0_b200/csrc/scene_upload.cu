@@ -97,6 +97,7 @@ int wrt_scene_create(const wrt_scene_desc* d, wrt_scene** out)
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreate(&sc->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&sc->ev1);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sc->ev_fork, cudaEventDisableTiming);
         if (e != cudaSuccess) { int rc = cuda_fail(e, "scene resources"); wrt_scene_destroy(sc); return rc; }
     }
     sc->view = L.view;
@@ -118,6 +119,7 @@ void wrt_scene_destroy(wrt_scene* sc)
     if (sc->stream) cudaStreamDestroy(sc->stream);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
+    if (sc->ev_fork) cudaEventDestroy(sc->ev_fork);
     delete sc;
 }
 

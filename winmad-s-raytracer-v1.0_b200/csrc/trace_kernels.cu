@@ -1,12 +1,12 @@
 // Level-1 ray queries behind the C ABI: batch equivalents of Scene::intersect(ray,inter),
 // Scene::intersect(ray), Scene::shadowRayTest and Scene::occluded (R/src/scene/scene.cpp:21-81).
 //
-// Launch shape: persistent warps.  The grid is (SM count x resident blocks per SM); each warp pulls
-// the next 32 consecutive rays from a global counter until the batch is exhausted, so long and short
-// rays balance across the machine without a tail of idle SMs.  One thread = one ray; the per-thread
-// traversal stack lives in local memory (L1-resident, lane-interleaved).
+// Launch shape: persistent warps with lane refill (trace_persistent.cuh).  The grid is (SM count x
+// resident blocks per SM); idle lanes claim new rays from a global counter while busy lanes keep
+// traversing, so long and short rays balance inside a warp and across the machine.  One thread = one
+// ray at a time; the per-thread traversal stack lives in local memory (L1-resident, lane-interleaved).
 #include <string>
-#include "traverse.cuh"
+#include "trace_persistent.cuh"
 #include "warp_utils.cuh"
 
 namespace wrt {
@@ -22,77 +22,101 @@ __device__ __forceinline__ RayIn load_ray(const wrt_ray* rays, size_t i)
     return r;
 }
 
-template <bool PRUNED>
-__global__ void __launch_bounds__(kTraceBlock)
-k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int32_t* __restrict__ prim,
-                float* __restrict__ t_out, float* __restrict__ p3, float* __restrict__ n3,
-                int32_t* __restrict__ inside, int32_t* __restrict__ matid, unsigned long long* counter)
+// Scene::shadowRayTest's verdict from a finished traversal (scene.cpp:58-68)
+__device__ __forceinline__ bool visible_from(const RayIn& r, int prim, float t, float px, float py, float pz)
 {
-    size_t base;
-    while (next_chunk(counter, n, base)) {
-        const size_t i = base + (threadIdx.x & 31);
-        if (i >= n) continue;
-        const RayIn r = load_ray(rays, i);
-        float t;
-        const int id = kd_traverse<PRUNED, false>(sc, r, t, nullptr);
+    if (prim < 0) return true;
+    const float ex = (r.ox + r.dx * t) - px, ey = (r.oy + r.dy * t) - py, ez = (r.oz + r.dz * t) - pz;
+    return !(ex < -WRT_EPS) && !(ex > WRT_EPS) && !(ey < -WRT_EPS) && !(ey > WRT_EPS) &&
+           !(ez < -WRT_EPS) && !(ez > WRT_EPS);
+}
+
+struct ClosestSrc {
+    const DevSceneView* sc;
+    const wrt_ray* rays; int32_t* prim; float* t_out; float* p3; float* n3; int32_t* inside; int32_t* matid;
+    __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
+    __device__ __forceinline__ void done(size_t i, const RayIn& r, int id, float t) const
+    {
         prim[i] = id;
         if (t_out) t_out[i] = t;
         if (p3 || n3 || inside || matid) {
             HitInfo h = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0, 0 };
-            if (id >= 0) fill_hit(sc, id, r, t, h);
+            if (id >= 0) fill_hit(*sc, id, r, t, h);
             if (p3) { p3[3 * i] = h.px; p3[3 * i + 1] = h.py; p3[3 * i + 2] = h.pz; }
             if (n3) { n3[3 * i] = h.nx; n3[3 * i + 1] = h.ny; n3[3 * i + 2] = h.nz; }
             if (inside) inside[i] = h.inside;
             if (matid) matid[i] = h.matid;
         }
     }
+};
+
+template <bool PRUNED>
+__global__ void __launch_bounds__(kTraceBlock)
+k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int32_t* __restrict__ prim,
+                float* __restrict__ t_out, float* __restrict__ p3, float* __restrict__ n3,
+                int32_t* __restrict__ inside, int32_t* __restrict__ matid, unsigned long long* counter)
+{
+    ClosestSrc src = { &sc, rays, prim, t_out, p3, n3, inside, matid };
+    trace_persistent<PRUNED>(sc, src, counter, n);
 }
+
+struct AnySrc {
+    const wrt_ray* rays; uint8_t* hit;
+    __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
+    __device__ __forceinline__ void done(size_t i, const RayIn&, int id, float) const { hit[i] = id >= 0 ? 1 : 0; }
+};
 
 template <bool PRUNED>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_any(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ hit,
             unsigned long long* counter)
 {
-    size_t base;
-    while (next_chunk(counter, n, base)) {
-        const size_t i = base + (threadIdx.x & 31);
-        if (i >= n) continue;
-        const RayIn r = load_ray(rays, i);
-        float t;
-        hit[i] = kd_traverse<PRUNED, false>(sc, r, t, nullptr) >= 0 ? 1 : 0;
-    }
+    AnySrc src = { rays, hit };
+    trace_persistent<PRUNED>(sc, src, counter, n);
 }
 
 // shadowRayTest: ray given, target point given; visible = 1.0f / 0.0f
+struct ShadowTestSrc {
+    const wrt_ray* rays; const float* target3; float* visible;
+    __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
+    __device__ __forceinline__ void done(size_t i, const RayIn& r, int id, float t) const
+    {
+        visible[i] = visible_from(r, id, t, target3[3 * i], target3[3 * i + 1], target3[3 * i + 2]) ? 1.0f : 0.0f;
+    }
+};
+
 template <bool PRUNED>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_shadow(DevSceneView sc, const wrt_ray* __restrict__ rays, const float* __restrict__ target3, size_t n,
                float* __restrict__ visible, unsigned long long* counter)
 {
-    size_t base;
-    while (next_chunk(counter, n, base)) {
-        const size_t i = base + (threadIdx.x & 31);
-        if (i >= n) continue;
-        const RayIn r = load_ray(rays, i);
-        visible[i] = shadow_visible<PRUNED>(sc, r, target3[3 * i], target3[3 * i + 1], target3[3 * i + 2]) ? 1.0f : 0.0f;
-    }
+    ShadowTestSrc src = { rays, target3, visible };
+    trace_persistent<PRUNED>(sc, src, counter, n);
 }
 
 // occluded(p1, dir, p2): builds Ray(p1, dir) (normalising dir) and negates shadowRayTest
+struct OccludedSrc {
+    const float* q9; uint8_t* occluded;
+    __device__ __forceinline__ bool load(size_t i, RayIn& r) const
+    {
+        const float* q = q9 + 9 * i;
+        make_ray(q[0], q[1], q[2], q[3], q[4], q[5], r);
+        return true;
+    }
+    __device__ __forceinline__ void done(size_t i, const RayIn& r, int id, float t) const
+    {
+        const float* q = q9 + 9 * i;
+        occluded[i] = visible_from(r, id, t, q[6], q[7], q[8]) ? 0 : 1;
+    }
+};
+
 template <bool PRUNED>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_occluded(DevSceneView sc, const float* __restrict__ q9, size_t n, uint8_t* __restrict__ occluded,
                  unsigned long long* counter)
 {
-    size_t base;
-    while (next_chunk(counter, n, base)) {
-        const size_t i = base + (threadIdx.x & 31);
-        if (i >= n) continue;
-        const float* q = q9 + 9 * i;
-        RayIn r;
-        make_ray(q[0], q[1], q[2], q[3], q[4], q[5], r);
-        occluded[i] = shadow_visible<PRUNED>(sc, r, q[6], q[7], q[8]) ? 0 : 1;
-    }
+    OccludedSrc src = { q9, occluded };
+    trace_persistent<PRUNED>(sc, src, counter, n);
 }
 
 __global__ void __launch_bounds__(kTraceBlock)

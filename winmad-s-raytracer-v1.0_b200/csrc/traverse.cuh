@@ -119,83 +119,116 @@ WRT_HD float bound_entry(const float4 a, const float4 b, const RayIn& r,
 
 #define WRT_PRUNE_REL 1.0001f
 
+// ---- traversal state machine ------------------------------------------------------------------------
+// One KDtreeAccel::traverse call, cut into the steps the kernels schedule: begin (root box, invDir),
+// visit a node (optional PRUNED skip), interior step (:325-358), leaf (:359-374), pop (:375-384).
+// kd_traverse() below runs them in a plain loop; the persistent kernels (trace_persistent.cuh) run the
+// SAME steps but let idle lanes of a warp pick up new rays in between.  Either way every ray performs
+// the same arithmetic in the same order.
+struct Trav {
+    float tmin, tmax, best;
+    float ix, iy, iz;     // invDir
+    int node, sp, res;
+};
+
+struct TravStack {
+    int node[WRT_STACK_DEPTH];
+    float tmin[WRT_STACK_DEPTH];
+    float tmax[WRT_STACK_DEPTH];
+};
+
+WRT_HD bool trav_begin(const DevSceneView& sc, const RayIn& r, Trav& T)
+{
+    if (!aabb_hit(sc.root_lo, sc.root_hi, r, T.tmin, T.tmax)) return false;     // :311-313
+    T.ix = 1.f / r.dx; T.iy = 1.f / r.dy; T.iz = 1.f / r.dz;                     // invDir, :315
+    T.node = 0; T.sp = 0; T.res = -1; T.best = WRT_INF;
+    return true;
+}
+
+template <bool PRUNED>
+WRT_HD bool trav_skip(const DevSceneView& sc, const float4 na, const RayIn& r, const Trav& T)
+{
+    if (PRUNED && T.res >= 0) {
+        const float4 nb = ldg4(&sc.nodes[2 * T.node + 1]);
+        return bound_entry(na, nb, r, T.ix, T.iy, T.iz) > T.best * WRT_PRUNE_REL;
+    }
+    return false;
+}
+
+WRT_HD void trav_interior(const float4 na, const RayIn& r, Trav& T, TravStack& S)
+{
+    const unsigned packed = f2u(na.y);
+    const int axis = (int)(packed & 3u);
+    const float split = na.x;
+    const float o_a = sel3(axis, r.ox, r.oy, r.oz);
+    const float d_a = sel3(axis, r.dx, r.dy, r.dz);
+    const float i_a = sel3(axis, T.ix, T.iy, T.iz);
+    const float t = (split - o_a) * i_a;                                          // :328
+    const bool below_first = (o_a < split) || (o_a == split && d_a <= 0.f);       // :331-332
+    const int pair = (int)(packed >> 2);
+    const int near_n = pair + (below_first ? 0 : 1);
+    const int far_n = pair + (below_first ? 1 : 0);
+    if (t > T.tmax || t <= 0.f) T.node = near_n;                                  // :345-346
+    else if (t < T.tmin) T.node = far_n;                                          // :347-348
+    else {                                                                        // :349-357
+        if (T.sp < WRT_STACK_DEPTH) { S.node[T.sp] = far_n; S.tmin[T.sp] = t; S.tmax[T.sp] = T.tmax; ++T.sp; }
+        T.node = near_n;
+        T.tmax = t;
+    }
+}
+
+template <bool COUNT>
+WRT_HD void trav_leaf(const DevSceneView& sc, const float4 na, const RayIn& r, Trav& T, VisitCounters* vc)
+{
+    const int first = f2i(na.x);
+    const int cnt = (int)(f2u(na.y) >> 2);
+    for (int i = 0; i < cnt; i++) {
+        const float4* rec = sc.leaf_recs + 3 * (size_t)(first + i);
+        const float4 r0 = ldg4(rec), r1 = ldg4(rec + 1), r2 = ldg4(rec + 2);
+        float t; bool hit;
+        if (f2i(r2.w) == 0) {
+            if (COUNT) vc->tri++;
+            hit = triangle_t(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, t);
+        } else {
+            if (COUNT) vc->sph++;
+            const float lo[3] = { r1.y, r1.z, r1.w }, hi[3] = { r2.x, r2.y, r2.z };
+            int inside;
+            hit = sphere_t(r0.x, r0.y, r0.z, r1.x, lo, hi, r, t, inside);
+        }
+        if (hit && (t - T.best < -WRT_EPS)) { T.best = t; T.res = f2i(r0.w); }    // :367-371
+    }
+}
+
+WRT_HD bool trav_pop(Trav& T, const TravStack& S)
+{
+    if (T.sp <= 0) return false;
+    --T.sp; T.node = S.node[T.sp]; T.tmin = S.tmin[T.sp]; T.tmax = S.tmax[T.sp];
+    return true;
+}
+
 // Returns the winning primitive id (index in Scene::objs) or -1, and its t in best_t.
 template <bool PRUNED, bool COUNT>
-WRT_HD int kd_traverse(const DevSceneView& sc, const RayIn& r, float& best_t,
-                                           VisitCounters* vc)
+WRT_HD int kd_traverse(const DevSceneView& sc, const RayIn& r, float& best_t, VisitCounters* vc)
 {
-    float tmin, tmax;
-    if (!aabb_hit(sc.root_lo, sc.root_hi, r, tmin, tmax)) { best_t = WRT_INF; return -1; }
-
-    const float ix = 1.f / r.dx, iy = 1.f / r.dy, iz = 1.f / r.dz;   // invDir, :315
-
-    int stack_node[WRT_STACK_DEPTH];
-    float stack_tmin[WRT_STACK_DEPTH];
-    float stack_tmax[WRT_STACK_DEPTH];
-    int sp = 0;
-    int res = -1;
-    float best = WRT_INF;
-    int node = 0;
-
+    Trav T;
+    TravStack S;
+    if (!trav_begin(sc, r, T)) { best_t = WRT_INF; return -1; }
     for (;;) {
-        if (r.tmax < tmin) break;                                      // :323
-        const float4 na = ldg4(&sc.nodes[2 * node]);
-        bool skip = false;
-        if (PRUNED && res >= 0) {
-            const float4 nb = ldg4(&sc.nodes[2 * node + 1]);
-            skip = bound_entry(na, nb, r, ix, iy, iz) > best * WRT_PRUNE_REL;
-        }
-        if (!skip) {
-            const unsigned packed = f2u(na.y);
-            const unsigned tag = packed & 3u;
-            if (tag != WRT_LEAF_TAG) {                                 // interior, :325-358
+        if (r.tmax < T.tmin) break;                                               // :323
+        const float4 na = ldg4(&sc.nodes[2 * T.node]);
+        if (!trav_skip<PRUNED>(sc, na, r, T)) {
+            if ((f2u(na.y) & 3u) != WRT_LEAF_TAG) {
                 if (COUNT) vc->inner++;
-                const int axis = (int)tag;
-                const float split = na.x;
-                const float o_a = sel3(axis, r.ox, r.oy, r.oz);
-                const float d_a = sel3(axis, r.dx, r.dy, r.dz);
-                const float i_a = sel3(axis, ix, iy, iz);
-                const float t = (split - o_a) * i_a;
-                const bool below_first = (o_a < split) || (o_a == split && d_a <= 0.f);
-                const int pair = (int)(packed >> 2);
-                const int near_n = pair + (below_first ? 0 : 1);
-                const int far_n = pair + (below_first ? 1 : 0);
-                if (t > tmax || t <= 0.f) node = near_n;
-                else if (t < tmin) node = far_n;
-                else {
-                    if (sp < WRT_STACK_DEPTH) {
-                        stack_node[sp] = far_n; stack_tmin[sp] = t; stack_tmax[sp] = tmax; ++sp;
-                    }
-                    node = near_n;
-                    tmax = t;
-                }
+                trav_interior(na, r, T, S);
                 continue;
             }
-            // leaf, :359-374
             if (COUNT) vc->leaf++;
-            const int first = f2i(na.x);
-            const int cnt = (int)(packed >> 2);
-            for (int i = 0; i < cnt; i++) {
-                const float4* rec = sc.leaf_recs + 3 * (size_t)(first + i);
-                const float4 r0 = ldg4(rec), r1 = ldg4(rec + 1), r2 = ldg4(rec + 2);
-                float t; bool hit;
-                if (f2i(r2.w) == 0) {
-                    if (COUNT) vc->tri++;
-                    hit = triangle_t(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, t);
-                } else {
-                    if (COUNT) vc->sph++;
-                    const float lo[3] = { r1.y, r1.z, r1.w }, hi[3] = { r2.x, r2.y, r2.z };
-                    int inside;
-                    hit = sphere_t(r0.x, r0.y, r0.z, r1.x, lo, hi, r, t, inside);
-                }
-                if (hit && (t - best < -WRT_EPS)) { best = t; res = f2i(r0.w); }   // :367-371
-            }
+            trav_leaf<COUNT>(sc, na, r, T, vc);
         }
-        if (sp > 0) { --sp; node = stack_node[sp]; tmin = stack_tmin[sp]; tmax = stack_tmax[sp]; }   // :375-384
-        else break;
+        if (!trav_pop(T, S)) break;
     }
-    best_t = (res >= 0) ? best : WRT_INF;
-    return res;
+    best_t = (T.res >= 0) ? T.best : WRT_INF;
+    return T.res;
 }
 
 // The rest of Intersection for the winner: Scene::intersect re-runs g->hit (scene.cpp:26-27).

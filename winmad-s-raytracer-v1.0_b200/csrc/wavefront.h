@@ -52,10 +52,13 @@ struct wrt_wavefront {
     void* bdpt;                         // BDPT-only buffers (bdpt_wavefront.cu)
     size_t bdpt_bytes;
     cudaEvent_t* ev; int n_ev;          // stage-timing events (4 per iteration)
+    cudaStream_t stream;                // this sub-pool's own stream (PT runs sub-pools concurrently)
+    cudaEvent_t join_ev;
 };
 
 namespace wrt {
 int wavefront_get(wrt_scene* sc, int capacity, wrt_wavefront** out);
+int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** out);
 int wavefront_film(wrt_scene* sc, size_t floats, float** out);
 int persistent_grid_for(const void* kernel, int block);
 int wavefront_events(wrt_wavefront* wf, int n);

@@ -4,6 +4,7 @@
 #pragma once
 #include "wavefront.h"
 #include "warp_utils.cuh"
+#include "trace_persistent.cuh"
 
 namespace wrt {
 
@@ -26,21 +27,23 @@ __device__ __forceinline__ void film_add(float* film, uint32_t pixel, V3 c, floa
     atomicAdd(&film[3 * (size_t)pixel + 2], c.z * scale);
 }
 
+struct ExtendSrc {
+    PathPool pool; const uint32_t* queue;
+    __device__ __forceinline__ bool load(size_t e, RayIn& r) const { r = pool_load_ray(pool, queue[e]); return true; }
+    __device__ __forceinline__ void done(size_t e, const RayIn&, int prim, float t) const
+    {
+        const uint32_t slot = queue[e];
+        pool.hit_prim[slot] = prim;
+        pool.hit_t[slot] = t;
+    }
+};
+
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock)
 k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters)
 {
-    size_t base;
-    while (next_chunk(&counters[WF_WORK], n, base)) {
-        const size_t e = base + (threadIdx.x & 31);
-        if (e >= n) continue;
-        const uint32_t slot = queue[e];
-        const RayIn r = pool_load_ray(pool, slot);
-        float t;
-        const int prim = kd_traverse<PRUNED, false>(sc, r, t, nullptr);
-        pool.hit_prim[slot] = prim;
-        pool.hit_t[slot] = t;
-    }
+    ExtendSrc src = { pool, queue };
+    trace_persistent<PRUNED>(sc, src, &counters[WF_WORK], n);
 }
 
 // Counting-mode variants: EXACT traversal with the reference-semantics visit counters.
@@ -92,21 +95,33 @@ k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, flo
     atomicAdd(&counters[WF_VISITS + 2], c); atomicAdd(&counters[WF_VISITS + 3], d);
 }
 
+struct ShadowSrc {
+    ShadowQueue sq; float* film; float scale;
+    __device__ __forceinline__ bool load(size_t e, RayIn& r) const
+    {
+        const float4 a = sq.a[e], b = sq.b[e];
+        make_ray(a.x, a.y, a.z, b.x, b.y, b.z, r);
+        return true;
+    }
+    __device__ __forceinline__ void done(size_t e, const RayIn& r, int prim, float t) const
+    {
+        const float4 c = sq.c[e];
+        bool vis = prim < 0;
+        if (!vis) {   // Scene::shadowRayTest: the hit point equals the target within EPS per component
+            const float ex = (r.ox + r.dx * t) - c.x, ey = (r.oy + r.dy * t) - c.y, ez = (r.oz + r.dz * t) - c.z;
+            vis = !(ex < -WRT_EPS) && !(ex > WRT_EPS) && !(ey < -WRT_EPS) && !(ey > WRT_EPS) && !(ez < -WRT_EPS) && !(ez > WRT_EPS);
+        }
+        if (vis) film_add(film, sq.pixel[e], v3(sq.a[e].w, sq.b[e].w, c.w), scale);
+    }
+};
+
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock)
 k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters)
 {
     const size_t n = (size_t)counters[WF_SHADOW_COUNT];
-    size_t base;
-    while (next_chunk(&counters[WF_WORK3], n, base)) {
-        const size_t e = base + (threadIdx.x & 31);
-        if (e >= n) continue;
-        const float4 a = sq.a[e], b = sq.b[e], c = sq.c[e];
-        RayIn r;
-        make_ray(a.x, a.y, a.z, b.x, b.y, b.z, r);
-        if (shadow_visible<PRUNED>(sc, r, c.x, c.y, c.z))
-            film_add(film, sq.pixel[e], v3(a.w, b.w, c.w), scale);
-    }
+    ShadowSrc src = { sq, film, scale };
+    trace_persistent<PRUNED>(sc, src, &counters[WF_WORK3], n);
 }
 
 }  // namespace wrt
