@@ -202,7 +202,7 @@ void fill_camera(const wrt_camera* c, DevCamera& d)
 static int pool_capacity()
 {
     const char* e = getenv("WRT_POOL_PATHS");
-    long v = e ? atol(e) : (1L << 23);
+    long v = e ? atol(e) : (1L << 24);
     if (v < 1024) v = 1024;
     if (v > (1L << 26)) v = 1L << 26;
     return (int)v;

@@ -57,7 +57,7 @@ k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int
                 int32_t* __restrict__ inside, int32_t* __restrict__ matid, unsigned long long* counter)
 {
     ClosestSrc src = { &sc, rays, prim, t_out, p3, n3, inside, matid };
-    trace_persistent<PRUNED>(sc, src, counter, n);
+    trace_rays<PRUNED>(sc, src, counter, n);
 }
 
 struct AnySrc {
@@ -72,7 +72,7 @@ k_trace_any(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, uint8_t
             unsigned long long* counter)
 {
     AnySrc src = { rays, hit };
-    trace_persistent<PRUNED>(sc, src, counter, n);
+    trace_rays<PRUNED>(sc, src, counter, n);
 }
 
 // shadowRayTest: ray given, target point given; visible = 1.0f / 0.0f
@@ -91,7 +91,7 @@ k_trace_shadow(DevSceneView sc, const wrt_ray* __restrict__ rays, const float* _
                float* __restrict__ visible, unsigned long long* counter)
 {
     ShadowTestSrc src = { rays, target3, visible };
-    trace_persistent<PRUNED>(sc, src, counter, n);
+    trace_rays<PRUNED>(sc, src, counter, n);
 }
 
 // occluded(p1, dir, p2): builds Ray(p1, dir) (normalising dir) and negates shadowRayTest
@@ -116,7 +116,7 @@ k_trace_occluded(DevSceneView sc, const float* __restrict__ q9, size_t n, uint8_
                  unsigned long long* counter)
 {
     OccludedSrc src = { q9, occluded };
-    trace_persistent<PRUNED>(sc, src, counter, n);
+    trace_rays<PRUNED>(sc, src, counter, n);
 }
 
 __global__ void __launch_bounds__(kTraceBlock)

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kBlock)
 k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters)
 {
     ExtendSrc src = { pool, queue };
-    trace_persistent<PRUNED>(sc, src, &counters[WF_WORK], n);
+    trace_rays<PRUNED>(sc, src, &counters[WF_WORK], n);
 }
 
 // Counting-mode variants: EXACT traversal with the reference-semantics visit counters.
@@ -121,7 +121,7 @@ k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float sca
 {
     const size_t n = (size_t)counters[WF_SHADOW_COUNT];
     ShadowSrc src = { sq, film, scale };
-    trace_persistent<PRUNED>(sc, src, &counters[WF_WORK3], n);
+    trace_rays<PRUNED>(sc, src, &counters[WF_WORK3], n);
 }
 
 }  // namespace wrt
