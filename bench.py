@@ -354,7 +354,7 @@ def main():
         "config": {"workload": w["desc"], "integrator": w["integrator"], "traversal": "pruned (bit-exact vs exact, tests/test_gpu_traversal.py)",
                    "per_gpu": "full frame, %d %s per GPU, disjoint RNG streams; films summed by one NCCL reduce" %
                               (w.get("spp", w.get("iterations")), "spp" if w["integrator"] == "pt" else "iterations"),
-                   "l2": "inputs larger than L2: the path pool (2^21 slots x 176 B) is rewritten every bounce; the scene is meant to stay L2-resident",
+                   "l2": "inputs larger than L2: the path pool (2^24 slots x 176 B in 2 concurrent sub-pools) is rewritten every bounce; the scene is meant to stay L2-resident",
                    "prims": int(sc.n_prims), "kd_build_s": round(kd_build_s, 2), "upload_s": round(upload_s, 2)},
         "samples_per_s": total_samples / (ms / 1e3), "rays_per_sample": rays / total_samples,
         "mean_radiance": mean_radiance,
@@ -375,6 +375,7 @@ def main():
         # traversal of the rays it traced / its own CUDA-event time
         achieved = (ext_rays * b_ray) / (ext_ms * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "k_pt_extend<pruned>", "achieved": achieved, "peak": peak,
+                            "note": "launch durations are CUDA-event times of launches that overlap with the other sub-pool's kernels (2 streams), so this is a lower bound of the kernel's stand-alone rate",
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "bytes_per_ray": b_ray, "visits_per_ray_reference_semantics": visits,

@@ -18,20 +18,78 @@ namespace wrt {
 
 constexpr int kRefillThreshold = 22;
 
+#ifndef WRT_FAST_DIV
+#define WRT_FAST_DIV 1
+#endif
+
+// Triangle::hit + the acceptance rule `t - best < -EPS`, answering only "does this triangle become the
+// new best, and with which t".  The reference only COMPARES beta, gamma and beta+gamma against
+// thresholds, and t against EPS, [tmin,tmax] and best-EPS; only a winning t is kept.  So the three IEEE
+// divisions are replaced by one reciprocal approximation (MUFU.RCP, ~1 ulp) whenever the quotient is far
+// from every threshold it is compared with (margin 1e-5 relative, >= 40x the approximation error);
+// numerators and the denominator are still the reference's exact no-FMA expressions.  Anything within
+// the margin, any NaN/inf and any extreme denominator takes the exact path (triangle_t), and a winning t
+// is always produced by the IEEE division, so results stay bit-identical (GPU tests compare >1e7 rays).
+__device__ __forceinline__ bool triangle_wins(float p0x, float p0y, float p0z, float A, float B, float C,
+                                              float D, float E, float F, const RayIn& r, float best, float& t_out)
+{
+#if WRT_FAST_DIV
+    const float G = r.dx, H = r.dy, I = r.dz;
+    const float J = p0x - r.ox, K = p0y - r.oy, L = p0z - r.oz;
+    const float EIHF = E * I - H * F;
+    const float GFDI = G * F - D * I;
+    const float DHEG = D * H - E * G;
+    const float denom = A * EIHF + B * GFDI + C * DHEG;
+    const float ad = fabsf(denom);
+    if (ad > 1e-30f && ad < 1e30f) {
+        float rd;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(denom));
+        const float bq = (J * EIHF + K * GFDI + L * DHEG) * rd;
+        const float mb = 1e-5f * fabsf(bq) + 2e-8f;
+        if (bq < -WRT_EPS - mb || bq > 1.f + mb) return false;                       // certainly rejected on beta
+        if (bq > -WRT_EPS + mb && bq < 1.f - mb) {                                   // certainly passes beta
+            const float AKJB = A * K - J * B;
+            const float JCAL = J * C - A * L;
+            const float BLKC = B * L - K * C;
+            const float gq = (I * AKJB + H * JCAL + G * BLKC) * rd;
+            const float mg = 1e-5f * fabsf(gq) + 2e-8f;
+            const float sum = bq + gq;
+            if (gq < -WRT_EPS - mg || sum > 1.f + 2e-5f) return false;               // certainly rejected on gamma
+            if (gq > -WRT_EPS + mg && sum < 1.f - 2e-5f) {                           // certainly inside
+                const float nt = -(F * AKJB + E * JCAL + D * BLKC);
+                const float tq = nt * rd;
+                const float mt = 1e-5f * fabsf(tq) + 1e-8f;
+                const float thr = best - WRT_EPS;
+                const float m2 = 1e-5f * (fabsf(tq) + fabsf(best)) + 1e-7f;
+                if (tq < WRT_EPS - mt || tq < r.tmin - mt || tq > r.tmax + mt || tq > thr + m2) return false;   // cannot win
+                if (tq > WRT_EPS + mt && tq > r.tmin + mt && tq < r.tmax - mt && tq < thr - m2) {
+                    t_out = nt / denom;                                              // the reference's t, IEEE division
+                    return true;
+                }
+            }
+        }
+    }
+#endif
+    float t;
+    if (!triangle_t(p0x, p0y, p0z, A, B, C, D, E, F, r, t)) return false;
+    if (!(t - best < -WRT_EPS)) return false;
+    t_out = t;
+    return true;
+}
+
 // One leaf record against the ray + the reference's acceptance rule (KDtreeAccel.cpp:363-373).
 __device__ __forceinline__ void leaf_record(const DevSceneView& sc, int rec_index, const RayIn& r, Trav& T)
 {
     const float4* rec = sc.leaf_recs + 3 * (size_t)rec_index;
     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-    float t; bool hit;
     if (__float_as_int(r2.w) == 0) {
-        hit = triangle_t(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, t);
+        float t;
+        if (triangle_wins(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, T.best, t)) { T.best = t; T.res = __float_as_int(r0.w); }
     } else {
         const float lo[3] = { r1.y, r1.z, r1.w }, hi[3] = { r2.x, r2.y, r2.z };
-        int inside;
-        hit = sphere_t(r0.x, r0.y, r0.z, r1.x, lo, hi, r, t, inside);
+        int inside; float t;
+        if (sphere_t(r0.x, r0.y, r0.z, r1.x, lo, hi, r, t, inside) && (t - T.best < -WRT_EPS)) { T.best = t; T.res = __float_as_int(r0.w); }
     }
-    if (hit && (t - T.best < -WRT_EPS)) { T.best = t; T.res = __float_as_int(r0.w); }
 }
 
 // Scheduler 2 ("vote"): every busy lane is either at a node or inside a leaf.  Each round the warp
@@ -47,7 +105,7 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
     TravStack S;
     RayIn r;
     size_t item = 0;
-    bool active = false, in_leaf = false;
+    bool active = false, in_leaf = false, need_pop = false;
     int rec = 0, rec_end = 0;
     bool exhausted = false;
     for (;;) {
@@ -65,7 +123,7 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
                     if (idx < n) {
                         item = idx;
                         if (src.load(idx, r)) {
-                            if (trav_begin(sc, r, T)) { active = true; in_leaf = false; }
+                            if (trav_begin(sc, r, T)) { active = true; in_leaf = false; need_pop = false; }
                             else src.done(idx, r, -1, WRT_INF);
                         }
                     }
@@ -81,105 +139,38 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
             const unsigned m_leaf = __ballot_sync(FULL, active && in_leaf);
             const int n_busy = __popc(m_busy), n_leaf = __popc(m_leaf);
             if (n_busy == 0 || (!exhausted && n_busy < kRefillThreshold)) break;
-            if (3 * n_leaf >= n_busy) {
-                // primitive round: one leaf record per lane that is inside a leaf
+            if (2 * n_leaf >= n_busy) {
+                // primitive round: up to two leaf records per lane that is inside a leaf.  A lane that
+                // exhausts its leaf only flags `need_pop`; the pop itself runs in the next node round,
+                // where most lanes do it together.
                 if (active && in_leaf) {
                     leaf_record(sc, rec, r, T);
-                    if (++rec == rec_end) {
-                        in_leaf = false;
-                        if (!trav_pop(T, S)) { src.done(item, r, T.res, (T.res >= 0) ? T.best : WRT_INF); active = false; }
+                    if (++rec == rec_end) { in_leaf = false; need_pop = true; }
+                    else {
+                        leaf_record(sc, rec, r, T);
+                        if (++rec == rec_end) { in_leaf = false; need_pop = true; }
                     }
                 }
             } else {
-                // node round: one node visit per lane that is at a node
+                // node round: (pop, then) one node visit per lane that is at a node
                 if (active && !in_leaf) {
                     bool finished = false;
-                    if (r.tmax < T.tmin) finished = true;                          // KDtreeAccel.cpp:323
-                    else {
-                        const float4 na = __ldg(&sc.nodes[2 * T.node]);
-                        if (trav_skip<PRUNED>(sc, na, r, T)) finished = !trav_pop(T, S);
-                        else if ((__float_as_uint(na.y) & 3u) == WRT_LEAF_TAG) {
-                            const int cnt = (int)(__float_as_uint(na.y) >> 2);
-                            if (cnt > 0) { in_leaf = true; rec = __float_as_int(na.x); rec_end = rec + cnt; }
-                            else finished = !trav_pop(T, S);
-                        } else trav_interior(na, r, T, S);
+                    if (need_pop) { need_pop = false; finished = !trav_pop(T, S); }
+                    if (!finished) {
+                        if (r.tmax < T.tmin) finished = true;                      // KDtreeAccel.cpp:323
+                        else {
+                            const float4 na = __ldg(&sc.nodes[2 * T.node]);
+                            if (trav_skip<PRUNED>(sc, na, r, T)) need_pop = true;
+                            else if ((__float_as_uint(na.y) & 3u) == WRT_LEAF_TAG) {
+                                const int cnt = (int)(__float_as_uint(na.y) >> 2);
+                                if (cnt > 0) { in_leaf = true; rec = __float_as_int(na.x); rec_end = rec + cnt; }
+                                else need_pop = true;
+                            } else trav_interior(na, r, T, S);
+                        }
                     }
                     if (finished) { src.done(item, r, T.res, (T.res >= 0) ? T.best : WRT_INF); active = false; }
                 }
             }
-        }
-    }
-}
-
-
-template <bool PRUNED, class Src>
-__device__ __forceinline__ void trace_persistent(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n)
-{
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31;
-    Trav T;
-    TravStack S;
-    RayIn r;
-    size_t item = 0;
-    bool active = false;
-    bool exhausted = false;     // warp-uniform: the counter ran past n
-    for (;;) {
-        if (!exhausted) {
-            const unsigned need = __ballot_sync(FULL, !active);
-            if (need) {
-                const int cnt = __popc(need);
-                const int leader = __ffs(need) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(counter, (unsigned long long)cnt);
-                base = __shfl_sync(FULL, base, leader);
-                if (base + (unsigned long long)cnt >= n) exhausted = true;
-                if (!active) {
-                    const size_t idx = (size_t)base + __popc(need & ((1u << lane) - 1u));
-                    if (idx < n) {
-                        item = idx;
-                        if (src.load(idx, r)) {
-                            if (trav_begin(sc, r, T)) active = true;
-                            else src.done(idx, r, -1, WRT_INF);
-                        }
-                    }
-                }
-            }
-        }
-        if (!__any_sync(FULL, active)) {
-            if (exhausted) break;
-            continue;
-        }
-        for (;;) {
-            // phase 1: every busy lane walks down to its next leaf (or finishes)
-            bool at_leaf = false;
-            float4 na = make_float4(0.f, 0.f, 0.f, 0.f);
-            while (active) {
-                if (r.tmax < T.tmin) {                                            // KDtreeAccel.cpp:323
-                    src.done(item, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
-                    active = false;
-                    break;
-                }
-                na = __ldg(&sc.nodes[2 * T.node]);
-                if (trav_skip<PRUNED>(sc, na, r, T)) {
-                    if (!trav_pop(T, S)) {
-                        src.done(item, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
-                        active = false;
-                    }
-                    continue;
-                }
-                if ((__float_as_uint(na.y) & 3u) == WRT_LEAF_TAG) { at_leaf = true; break; }
-                trav_interior(na, r, T, S);
-            }
-            // phase 2: every busy lane intersects its leaf, then pops
-            if (active && at_leaf) {
-                trav_leaf<false>(sc, na, r, T, nullptr);
-                if (!trav_pop(T, S)) {
-                    src.done(item, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
-                    active = false;
-                }
-            }
-            const int busy = __popc(__ballot_sync(FULL, active));
-            if (busy == 0 || (!exhausted && busy < kRefillThreshold)) break;
         }
     }
 }
