@@ -60,6 +60,9 @@ def build(force=False, verbose_ptxas=False):
         objs.append(o)
     if force or _newer(LIB, objs):
         _run([NVCC, "-shared", "-o", LIB] + objs)  # nvcc links the static cudart by default
+    cli = os.path.join(HERE, "wrt_tot")
+    if force or _newer(cli, [os.path.join(HERE, "host/main.cpp"), LIB]):
+        _run([CXX] + CXX_FLAGS + ["-o", cli, "host/main.cpp", "-L", HERE, "-lwrt_b200", "-Wl,-rpath," + HERE])
     return LIB
 
 

@@ -321,8 +321,8 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
                 WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), st));
                 if (ev) cudaEventRecord(ev[0], st);
                 if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
+                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
                 if (ev) cudaEventRecord(ev[1], st);
                 if (phase == 0)
                     k_bdpt_light_shade<<<g_ls, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, Bv, wf->queue[cur], n, wf->queue[cur ^ 1], wf->counters);
@@ -330,8 +330,8 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
                     k_bdpt_camera_shade<<<g_cs, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[cur], n, wf->queue[cur ^ 1], d_film, wf->counters);
                 if (ev) cudaEventRecord(ev[2], st);
                 if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
-                else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
-                else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
+                else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
+                else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
                 if (phase == 1) {
                     if (pruned) k_bdpt_di<true><<<g_di_p, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters);
                     else k_bdpt_di<false><<<g_di_e, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters);

@@ -69,6 +69,7 @@ struct wrt_scene {
     void* d_scratch_in; size_t scratch_in_bytes;
     void* d_scratch_out; size_t scratch_out_bytes;
     unsigned long long* d_counters;  // small device counter block
+    void* d_trav_scratch; size_t trav_scratch_bytes;   // pooled scheduler's traversal stacks (API calls on `stream`)
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev_fork;
     struct wrt_wavefront* wf;        // lazily created integrator state (sub-pool 0; owns the film and BDPT buffers)
@@ -80,6 +81,7 @@ void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what);
 #define WRT_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return wrt::cuda_fail(e__, #call); } while (0)
 int ensure_scratch(wrt_scene* sc, size_t in_bytes, size_t out_bytes);
+int ensure_trav_scratch(void** ptr, size_t* bytes);
 void wavefront_destroy(wrt_scene* sc);
 }  // namespace wrt
 #endif  // __CUDACC__

@@ -38,9 +38,19 @@ struct ShadeOut {
 WRT_HD void pt_generate(const PtParams& P, const DevCamera& cam, unsigned long long s, RayIn& ray, PathData& pd)
 {
     const unsigned long long npix = (unsigned long long)P.width * P.height;
-    const uint32_t pixel = (uint32_t)(s % npix);
+    const uint32_t lin = (uint32_t)(s % npix);
     const int k = P.sample_first + (int)(s / npix) * P.sample_stride;
-    const int i = (int)(pixel / (uint32_t)P.width), j = (int)(pixel % (uint32_t)P.width);
+    // Consecutive samples walk the image in 8x4 pixel tiles (one warp = one tile) when the size allows:
+    // neighbouring rays share nodes and leaves.  The RNG is keyed on the pixel, so the image is unchanged.
+    int i, j;
+    if ((P.width & 7) == 0 && (P.height & 3) == 0) {
+        const uint32_t tile = lin >> 5, within = lin & 31u, tiles_x = (uint32_t)P.width >> 3;
+        j = (int)((tile % tiles_x) * 8u + (within & 7u));
+        i = (int)((tile / tiles_x) * 4u + (within >> 3));
+    } else {
+        i = (int)(lin / (uint32_t)P.width); j = (int)(lin % (uint32_t)P.width);
+    }
+    const uint32_t pixel = (uint32_t)i * (uint32_t)P.width + (uint32_t)j;
     pd.rng = rng_make(P.seed, 0u, (unsigned long long)k * npix + pixel);
     const V3 u = rng_vec3(pd.rng);
     const int len = P.strata;

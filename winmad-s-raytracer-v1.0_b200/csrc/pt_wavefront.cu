@@ -121,6 +121,7 @@ int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** ou
     WRT_CUDA(cudaMalloc((void**)&wf->counters, WF_COUNTERS * sizeof(unsigned long long)));
     WRT_CUDA(cudaMallocHost((void**)&wf->h_counters, WF_COUNTERS * sizeof(unsigned long long)));
     WRT_CUDA(cudaStreamCreateWithFlags(&wf->stream, cudaStreamNonBlocking));
+    { int rc = ensure_trav_scratch(&wf->trav_scratch, &wf->trav_scratch_bytes); if (rc) return rc; }
     WRT_CUDA(cudaEventCreateWithFlags(&wf->join_ev, cudaEventDisableTiming));
     *out = wf;
     return WRT_OK;
@@ -176,7 +177,7 @@ static void wavefront_free(wrt_wavefront* wf)
     cudaFree(wf->pool.hit_prim); cudaFree(wf->pool.hit_t);
     cudaFree(wf->queue[0]); cudaFree(wf->queue[1]);
     cudaFree(wf->shadow.a); cudaFree(wf->shadow.b); cudaFree(wf->shadow.c); cudaFree(wf->shadow.pixel);
-    cudaFree(wf->counters); cudaFreeHost(wf->h_counters); cudaFree(wf->film);
+    cudaFree(wf->counters); cudaFreeHost(wf->h_counters); cudaFree(wf->film); cudaFree(wf->trav_scratch);
     for (int i = 0; i < wf->n_ev; i++) cudaEventDestroy(wf->ev[i]);
     delete[] wf->ev;
     if (wf->stream) cudaStreamDestroy(wf->stream);
@@ -312,15 +313,15 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), q));
         if (ev) cudaEventRecord(ev[0], q);
         if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
+        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
         if (ev) cudaEventRecord(ev[1], q);
         k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
                                               d_film, wf->counters, next_sample);
         if (ev) cudaEventRecord(ev[2], q);
         if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
-        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
-        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
+        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
         if (ev) { cudaEventRecord(ev[3], q); s.timed++; }
         WRT_CUDA(cudaGetLastError());
         WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters, WF_PER_ITER * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q));

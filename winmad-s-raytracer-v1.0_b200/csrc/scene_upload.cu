@@ -115,7 +115,7 @@ void wrt_scene_destroy(wrt_scene* sc)
     wavefront_destroy(sc);
     cudaFree(sc->d_nodes); cudaFree(sc->d_leaf_recs); cudaFree(sc->d_prims);
     cudaFree(sc->d_materials); cudaFree(sc->d_lights);
-    cudaFree(sc->d_scratch_in); cudaFree(sc->d_scratch_out); cudaFree(sc->d_counters);
+    cudaFree(sc->d_scratch_in); cudaFree(sc->d_scratch_out); cudaFree(sc->d_counters); cudaFree(sc->d_trav_scratch);
     if (sc->stream) cudaStreamDestroy(sc->stream);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);

@@ -6,12 +6,13 @@
 // traversing, so long and short rays balance inside a warp and across the machine.  One thread = one
 // ray at a time; the per-thread traversal stack lives in local memory (L1-resident, lane-interleaved).
 #include <string>
-#include "trace_persistent.cuh"
+#include "trace_pooled.cuh"
 #include "warp_utils.cuh"
 
 namespace wrt {
 
 constexpr int kTraceBlock = 128;
+constexpr int kMaxBlocksPerSm = 12;
 
 __device__ __forceinline__ RayIn load_ray(const wrt_ray* rays, size_t i)
 {
@@ -54,10 +55,10 @@ template <bool PRUNED>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int32_t* __restrict__ prim,
                 float* __restrict__ t_out, float* __restrict__ p3, float* __restrict__ n3,
-                int32_t* __restrict__ inside, int32_t* __restrict__ matid, unsigned long long* counter)
+                int32_t* __restrict__ inside, int32_t* __restrict__ matid, unsigned long long* counter, float4* scratch)
 {
     ClosestSrc src = { &sc, rays, prim, t_out, p3, n3, inside, matid };
-    trace_rays<PRUNED>(sc, src, counter, n);
+    trace_rays<PRUNED>(sc, src, counter, n, scratch);
 }
 
 struct AnySrc {
@@ -69,10 +70,10 @@ struct AnySrc {
 template <bool PRUNED>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_any(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ hit,
-            unsigned long long* counter)
+            unsigned long long* counter, float4* scratch)
 {
     AnySrc src = { rays, hit };
-    trace_rays<PRUNED>(sc, src, counter, n);
+    trace_rays<PRUNED>(sc, src, counter, n, scratch);
 }
 
 // shadowRayTest: ray given, target point given; visible = 1.0f / 0.0f
@@ -88,10 +89,10 @@ struct ShadowTestSrc {
 template <bool PRUNED>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_shadow(DevSceneView sc, const wrt_ray* __restrict__ rays, const float* __restrict__ target3, size_t n,
-               float* __restrict__ visible, unsigned long long* counter)
+               float* __restrict__ visible, unsigned long long* counter, float4* scratch)
 {
     ShadowTestSrc src = { rays, target3, visible };
-    trace_rays<PRUNED>(sc, src, counter, n);
+    trace_rays<PRUNED>(sc, src, counter, n, scratch);
 }
 
 // occluded(p1, dir, p2): builds Ray(p1, dir) (normalising dir) and negates shadowRayTest
@@ -113,10 +114,10 @@ struct OccludedSrc {
 template <bool PRUNED>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_occluded(DevSceneView sc, const float* __restrict__ q9, size_t n, uint8_t* __restrict__ occluded,
-                 unsigned long long* counter)
+                 unsigned long long* counter, float4* scratch)
 {
     OccludedSrc src = { q9, occluded };
-    trace_rays<PRUNED>(sc, src, counter, n);
+    trace_rays<PRUNED>(sc, src, counter, n, scratch);
 }
 
 __global__ void __launch_bounds__(kTraceBlock)
@@ -137,13 +138,32 @@ k_count_visits(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, unsi
     atomicAdd(&sums[0], a); atomicAdd(&sums[1], b); atomicAdd(&sums[2], c); atomicAdd(&sums[3], d);
 }
 
+int ensure_trav_scratch(void** ptr, size_t* bytes)
+{
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t need = trav_scratch_bytes(sms * kMaxBlocksPerSm, kTraceBlock);
+    if (*bytes >= need) return WRT_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *bytes = 0;
+    WRT_CUDA(cudaMalloc(ptr, need));
+    *bytes = need;
+    return WRT_OK;
+}
+
 int persistent_grid_for(const void* kernel, int block)
 {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#if WRT_TRACE_SCHED != 3
+    // traversal is bound by L1TEX: give the kernels the whole unified cache as L1
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+#endif
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
     if (per_sm < 1) per_sm = 1;
+    if (per_sm > kMaxBlocksPerSm) per_sm = kMaxBlocksPerSm;   // the traversal scratch is sized for this many
     return sms * per_sm;
 }
 
@@ -155,10 +175,10 @@ static int launch_closest(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_
     WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
     if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
         static int grid = persistent_grid_for((const void*)k_trace_closest<true>, kTraceBlock);
-        k_trace_closest<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, sc->d_counters);
+        k_trace_closest<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, sc->d_counters, (float4*)sc->d_trav_scratch);
     } else {
         static int grid = persistent_grid_for((const void*)k_trace_closest<false>, kTraceBlock);
-        k_trace_closest<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, sc->d_counters);
+        k_trace_closest<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, sc->d_counters, (float4*)sc->d_trav_scratch);
     }
     WRT_CUDA(cudaGetLastError());
     sc->stats.closest_rays += n;
@@ -172,10 +192,10 @@ static int launch_occluded(wrt_scene* sc, const float* d_q9, size_t n, uint8_t* 
     WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
     if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
         static int grid = persistent_grid_for((const void*)k_trace_occluded<true>, kTraceBlock);
-        k_trace_occluded<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, sc->d_counters);
+        k_trace_occluded<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, sc->d_counters, (float4*)sc->d_trav_scratch);
     } else {
         static int grid = persistent_grid_for((const void*)k_trace_occluded<false>, kTraceBlock);
-        k_trace_occluded<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, sc->d_counters);
+        k_trace_occluded<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, sc->d_counters, (float4*)sc->d_trav_scratch);
     }
     WRT_CUDA(cudaGetLastError());
     sc->stats.shadow_rays += n;
@@ -188,7 +208,8 @@ static int launch_occluded(wrt_scene* sc, const float* d_q9, size_t n, uint8_t* 
 using namespace wrt;
 
 #define CHECK_SCENE(sc) do { if (!(sc)) { set_error("null scene"); return WRT_ERR_INVALID; } \
-    WRT_CUDA(cudaSetDevice((sc)->device)); } while (0)
+    WRT_CUDA(cudaSetDevice((sc)->device)); \
+    { int rc__ = ensure_trav_scratch(&(sc)->d_trav_scratch, &(sc)->trav_scratch_bytes); if (rc__) return rc__; } } while (0)
 
 extern "C" {
 
@@ -242,10 +263,10 @@ int wrt_trace_any(wrt_scene* sc, const wrt_ray* rays, size_t n, uint8_t* hit)
     WRT_CUDA(cudaEventRecord(sc->ev0, st));
     if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
         static int grid = persistent_grid_for((const void*)k_trace_any<true>, kTraceBlock);
-        k_trace_any<true><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, sc->d_counters);
+        k_trace_any<true><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, sc->d_counters, (float4*)sc->d_trav_scratch);
     } else {
         static int grid = persistent_grid_for((const void*)k_trace_any<false>, kTraceBlock);
-        k_trace_any<false><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, sc->d_counters);
+        k_trace_any<false><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, sc->d_counters, (float4*)sc->d_trav_scratch);
     }
     WRT_CUDA(cudaGetLastError());
     sc->stats.closest_rays += n; sc->stats.kernel_launches += 1;
@@ -272,10 +293,10 @@ int wrt_trace_shadow(wrt_scene* sc, const wrt_ray* rays, const float* target3, s
     WRT_CUDA(cudaEventRecord(sc->ev0, st));
     if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
         static int grid = persistent_grid_for((const void*)k_trace_shadow<true>, kTraceBlock);
-        k_trace_shadow<true><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)in, d_target, n, (float*)sc->d_scratch_out, sc->d_counters);
+        k_trace_shadow<true><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)in, d_target, n, (float*)sc->d_scratch_out, sc->d_counters, (float4*)sc->d_trav_scratch);
     } else {
         static int grid = persistent_grid_for((const void*)k_trace_shadow<false>, kTraceBlock);
-        k_trace_shadow<false><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)in, d_target, n, (float*)sc->d_scratch_out, sc->d_counters);
+        k_trace_shadow<false><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)in, d_target, n, (float*)sc->d_scratch_out, sc->d_counters, (float4*)sc->d_trav_scratch);
     }
     WRT_CUDA(cudaGetLastError());
     sc->stats.shadow_rays += n; sc->stats.kernel_launches += 1;

@@ -16,7 +16,10 @@
 
 namespace wrt {
 
-constexpr int kRefillThreshold = 22;
+#ifndef WRT_REFILL_THRESHOLD
+#define WRT_REFILL_THRESHOLD 28
+#endif
+constexpr int kRefillThreshold = WRT_REFILL_THRESHOLD;
 
 #ifndef WRT_FAST_DIV
 #define WRT_FAST_DIV 1
@@ -165,7 +168,8 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
                                 const int cnt = (int)(__float_as_uint(na.y) >> 2);
                                 if (cnt > 0) { in_leaf = true; rec = __float_as_int(na.x); rec_end = rec + cnt; }
                                 else need_pop = true;
-                            } else trav_interior(na, r, T, S);
+                            } else if (PRUNED) trav_interior_prune(sc, na, r, T, S);
+                            else trav_interior(na, r, T, S);
                         }
                     }
                     if (finished) { src.done(item, r, T.res, (T.res >= 0) ? T.best : WRT_INF); active = false; }
@@ -173,20 +177,6 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
             }
         }
     }
-}
-
-// Compile-time choice of the scheduler used by the kernels (A/B measured in profiles/).
-#ifndef WRT_TRACE_SCHED
-#define WRT_TRACE_SCHED 2
-#endif
-template <bool PRUNED, class Src>
-__device__ __forceinline__ void trace_rays(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n)
-{
-#if WRT_TRACE_SCHED == 2
-    trace_persistent_vote<PRUNED>(sc, src, counter, n);
-#else
-    trace_persistent<PRUNED>(sc, src, counter, n);
-#endif
 }
 
 }  // namespace wrt

@@ -1,0 +1,231 @@
+// Pooled traversal (scheduler 3): a warp owns a pool of kPoolRays rays whose traversal state lives in
+// shared memory, and three FIFO rings of slot ids — rays waiting for a node visit, rays waiting for
+// primitive tests, free slots.  Each round the warp serves the longer ring: lane l takes the l-th
+// waiting ray, loads its state (a few LDS.128), performs one unit of work (<= kNodeSteps node visits or
+// <= kPrimSteps leaf records) and re-queues the ray on the ring it now belongs to (ballot/popc
+// positions).  Because there are twice as many rays as lanes, both kinds of round normally run with all
+// 32 lanes, instead of ~40 % of them when every lane is married to one ray (profiles/r1_ncu_extend_*).
+// Free slots are refilled from the global work counter in batches.
+//
+// The per-ray steps are exactly those of traverse.cuh / trace_persistent.cuh (trav_begin, trav_skip,
+// trav_interior arithmetic, leaf_record, pop), executed in the same order for every ray, so results are
+// bit-identical to kd_traverse().  Only the traversal stack moves: it lives in a per-warp global
+// scratch area ([depth][slot], 16-byte entries) because any lane may continue any ray.
+#pragma once
+#include "trace_persistent.cuh"
+
+namespace wrt {
+
+constexpr int kPoolRays = 64;          // rays per warp (power of two)
+constexpr int kPoolStack = 32;         // stack entries per ray (reference: depMax + 5, <= 29 for 1e8 primitives)
+constexpr int kNodeSteps = 2;
+constexpr int kPrimSteps = 2;
+constexpr unsigned kMinRefill = 16;
+
+struct PoolSmem {
+    float4 a[kPoolRays];               // ox oy oz dx
+    float4 b[kPoolRays];               // dy dz ray.tmin ray.tmax
+    float4 c[kPoolRays];               // ix iy iz best
+    float4 d[kPoolRays];               // T.tmin T.tmax node(int) sp|need_pop<<30 (int)
+    int4 e[kPoolRays];                 // res rec rec_end item
+    unsigned char ring[3][kPoolRays];  // 0 node, 1 prim, 2 free
+};
+
+constexpr size_t kPoolStackBytesPerWarp = (size_t)kPoolStack * kPoolRays * sizeof(float4);
+
+template <bool PRUNED, class Src>
+__device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n,
+                                             PoolSmem& sm, float4* __restrict__ gstack)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned RM = kPoolRays - 1;
+    unsigned hn = 0, tn = 0, hp = 0, tp = 0, hf = 0, tf = kPoolRays;   // ring heads / tails (monotonic)
+    for (unsigned i = lane; i < (unsigned)kPoolRays; i += 32) sm.ring[2][i] = (unsigned char)i;
+    __syncwarp();
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- refill free slots from the global work counter ------------------------------------
+        unsigned nfree = tf - hf;
+        if (!exhausted && nfree >= kMinRefill) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)nfree);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + nfree >= n) exhausted = true;
+            for (unsigned k0 = 0; k0 < nfree; k0 += 32) {
+                const unsigned k = k0 + lane;
+                const bool have = k < nfree;
+                unsigned slot = 0;
+                if (have) slot = sm.ring[2][(hf + k) & RM];
+                __syncwarp();
+                bool started = false;
+                const size_t item = (size_t)base + k;
+                if (have && item < n) {
+                    RayIn r;
+                    if (src.load(item, r)) {
+                        Trav T;
+                        if (trav_begin(sc, r, T)) {
+                            sm.a[slot] = make_float4(r.ox, r.oy, r.oz, r.dx);
+                            sm.b[slot] = make_float4(r.dy, r.dz, r.tmin, r.tmax);
+                            sm.c[slot] = make_float4(T.ix, T.iy, T.iz, T.best);
+                            sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(0), __int_as_float(0));
+                            sm.e[slot] = make_int4(-1, 0, 0, (int)item);
+                            started = true;
+                        } else src.done(item, r, -1, WRT_INF);
+                    }
+                }
+                const unsigned bs = __ballot_sync(FULL, started);
+                if (started) sm.ring[0][(tn + __popc(bs & lt)) & RM] = (unsigned char)slot;
+                tn += __popc(bs);
+                const unsigned bf = __ballot_sync(FULL, have && !started);
+                if (have && !started) sm.ring[2][(tf + __popc(bf & lt)) & RM] = (unsigned char)slot;
+                tf += __popc(bf);
+            }
+            hf += nfree;
+            __syncwarp();
+        }
+        const unsigned cn = tn - hn, cp = tp - hp;
+        if (cn + cp == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        if (cp >= cn) {
+            // ---- primitive round ----------------------------------------------------------------
+            const unsigned cnt = cp < 32u ? cp : 32u;
+            const bool have = lane < cnt;
+            unsigned slot = 0;
+            if (have) slot = sm.ring[1][(hp + lane) & RM];
+            hp += cnt;
+            __syncwarp();
+            bool leaf_done = false;
+            if (have) {
+                const float4 a = sm.a[slot], b = sm.b[slot];
+                RayIn r; r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
+                int4 e = sm.e[slot];
+                Trav T; T.best = sm.c[slot].w; T.res = e.x;
+                const float best0 = T.best;
+#pragma unroll
+                for (int s = 0; s < kPrimSteps; s++) {
+                    leaf_record(sc, e.y, r, T);
+                    if (++e.y == e.z) { leaf_done = true; break; }
+                }
+                if (T.best != best0) { sm.c[slot].w = T.best; }
+                e.x = T.res;
+                sm.e[slot] = e;
+                if (leaf_done) sm.d[slot].w = __int_as_float(__float_as_int(sm.d[slot].w) | (1 << 30));   // need_pop
+            }
+            const unsigned b1 = __ballot_sync(FULL, have && !leaf_done);
+            if (have && !leaf_done) sm.ring[1][(tp + __popc(b1 & lt)) & RM] = (unsigned char)slot;
+            tp += __popc(b1);
+            const unsigned b0 = __ballot_sync(FULL, have && leaf_done);
+            if (have && leaf_done) sm.ring[0][(tn + __popc(b0 & lt)) & RM] = (unsigned char)slot;
+            tn += __popc(b0);
+            __syncwarp();
+        } else {
+            // ---- node round ---------------------------------------------------------------------
+            const unsigned cnt = cn < 32u ? cn : 32u;
+            const bool have = lane < cnt;
+            unsigned slot = 0;
+            if (have) slot = sm.ring[0][(hn + lane) & RM];
+            hn += cnt;
+            __syncwarp();
+            int next = 0;     // 0 stays on the node ring, 1 moves to the prim ring, 2 finished
+            if (have) {
+                const float4 a = sm.a[slot], b = sm.b[slot], c = sm.c[slot], d = sm.d[slot];
+                RayIn r; r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
+                Trav T; T.ix = c.x; T.iy = c.y; T.iz = c.z; T.best = c.w; T.tmin = d.x; T.tmax = d.y;
+                T.node = __float_as_int(d.z);
+                const int spw = __float_as_int(d.w);
+                T.sp = spw & 0xffff;
+                bool need_pop = (spw >> 30) & 1;
+                int4 e = sm.e[slot];
+                T.res = e.x;
+                float4* stk = gstack + slot;                      // entry (sp, slot) at stk[sp * kPoolRays]
+                for (int s = 0; s < kNodeSteps; s++) {
+                    if (need_pop) {
+                        need_pop = false;
+                        if (T.sp <= 0) { next = 2; break; }
+                        --T.sp;
+                        const float4 q = stk[(size_t)T.sp * kPoolRays];
+                        T.node = __float_as_int(q.x); T.tmin = q.y; T.tmax = q.z;
+                    }
+                    if (r.tmax < T.tmin) { next = 2; break; }                              // KDtreeAccel.cpp:323
+                    const float4 na = __ldg(&sc.nodes[2 * T.node]);
+                    if (trav_skip<PRUNED>(sc, na, r, T)) { need_pop = true; continue; }
+                    const unsigned packed = __float_as_uint(na.y);
+                    if ((packed & 3u) == WRT_LEAF_TAG) {
+                        const int cntl = (int)(packed >> 2);
+                        if (cntl > 0) { e.y = __float_as_int(na.x); e.z = e.y + cntl; next = 1; break; }
+                        need_pop = true;
+                        continue;
+                    }
+                    // interior step: trav_interior with the push going to the global scratch stack
+                    const int axis = (int)(packed & 3u);
+                    const float split = na.x;
+                    const float o_a = sel3(axis, r.ox, r.oy, r.oz);
+                    const float d_a = sel3(axis, r.dx, r.dy, r.dz);
+                    const float i_a = sel3(axis, T.ix, T.iy, T.iz);
+                    const float t = (split - o_a) * i_a;
+                    const bool below_first = (o_a < split) || (o_a == split && d_a <= 0.f);
+                    const int pair = (int)(packed >> 2);
+                    const int near_n = pair + (below_first ? 0 : 1);
+                    const int far_n = pair + (below_first ? 1 : 0);
+                    if (t > T.tmax || t <= 0.f) T.node = near_n;
+                    else if (t < T.tmin) T.node = far_n;
+                    else {
+                        if (T.sp < kPoolStack) { stk[(size_t)T.sp * kPoolRays] = make_float4(__int_as_float(far_n), t, T.tmax, 0.f); ++T.sp; }
+                        T.node = near_n;
+                        T.tmax = t;
+                    }
+                }
+                if (next == 2) {
+                    src.done((size_t)(unsigned)e.w, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
+                } else {
+                    sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(T.node), __int_as_float(T.sp | (need_pop ? (1 << 30) : 0)));
+                    if (next == 1) sm.e[slot] = e;
+                }
+            }
+            const unsigned b0 = __ballot_sync(FULL, have && next == 0);
+            if (have && next == 0) sm.ring[0][(tn + __popc(b0 & lt)) & RM] = (unsigned char)slot;
+            tn += __popc(b0);
+            const unsigned b1 = __ballot_sync(FULL, have && next == 1);
+            if (have && next == 1) sm.ring[1][(tp + __popc(b1 & lt)) & RM] = (unsigned char)slot;
+            tp += __popc(b1);
+            const unsigned b2 = __ballot_sync(FULL, have && next == 2);
+            if (have && next == 2) sm.ring[2][(tf + __popc(b2 & lt)) & RM] = (unsigned char)slot;
+            tf += __popc(b2);
+            __syncwarp();
+        }
+    }
+}
+
+// Compile-time choice of the scheduler used by the kernels (A/B measured in profiles/):
+// 1 = lane refill + while-while, 2 = lane refill + vote (default: fastest measured, profiles/), 3 = pooled.
+#ifndef WRT_TRACE_SCHED
+#define WRT_TRACE_SCHED 2
+#endif
+template <bool PRUNED, class Src>
+__device__ __forceinline__ void trace_rays(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n,
+                                           float4* trav_scratch)
+{
+#if WRT_TRACE_SCHED == 3
+    __shared__ PoolSmem pool_smem[4];                       // kernels launch 128 threads = 4 warps
+    const unsigned warp = threadIdx.x >> 5;
+    float4* stk = trav_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * ((size_t)kPoolStack * kPoolRays);
+    trace_pooled<PRUNED>(sc, src, counter, n, pool_smem[warp], stk);
+#elif WRT_TRACE_SCHED == 2
+    trace_persistent_vote<PRUNED>(sc, src, counter, n);
+#else
+    trace_persistent<PRUNED>(sc, src, counter, n);
+#endif
+}
+
+// Global scratch for the pooled scheduler's traversal stacks: one region per resident warp of a launch.
+inline size_t trav_scratch_bytes(int grid_blocks, int block_threads)
+{
+    return (size_t)grid_blocks * (size_t)(block_threads / 32) * kPoolStackBytesPerWarp;
+}
+
+}  // namespace wrt

@@ -131,10 +131,8 @@ struct Trav {
     int node, sp, res;
 };
 
-struct TravStack {
-    int node[WRT_STACK_DEPTH];
-    float tmin[WRT_STACK_DEPTH];
-    float tmax[WRT_STACK_DEPTH];
+struct TravStack {            // KDTodo (KDtreeAccel.h:47-51): one 16-byte entry = one local-memory access
+    float4 e[WRT_STACK_DEPTH];    // node (int bits), tmin, tmax, unused
 };
 
 WRT_HD bool trav_begin(const DevSceneView& sc, const RayIn& r, Trav& T)
@@ -171,7 +169,42 @@ WRT_HD void trav_interior(const float4 na, const RayIn& r, Trav& T, TravStack& S
     if (t > T.tmax || t <= 0.f) T.node = near_n;                                  // :345-346
     else if (t < T.tmin) T.node = far_n;                                          // :347-348
     else {                                                                        // :349-357
-        if (T.sp < WRT_STACK_DEPTH) { S.node[T.sp] = far_n; S.tmin[T.sp] = t; S.tmax[T.sp] = T.tmax; ++T.sp; }
+        if (T.sp < WRT_STACK_DEPTH) { S.e[T.sp] = make_float4(i2f(far_n), t, T.tmax, 0.f); ++T.sp; }
+        T.node = near_n;
+        T.tmax = t;
+    }
+}
+
+// PRUNED traversal only: same step as trav_interior, but a far child whose conservative bounds already
+// fail the prune test is not pushed at all.  `best` only ever decreases, so a sub-tree that is prunable
+// now is prunable when it would have been popped: dropping it here removes a push, a pop and a node
+// fetch without changing any state the reference would have.  The far child is the near child's
+// neighbour in memory (sibling pairs are adjacent), so its bounds share the cache line fetched next.
+WRT_HD void trav_interior_prune(const DevSceneView& sc, const float4 na, const RayIn& r, Trav& T, TravStack& S)
+{
+    const unsigned packed = f2u(na.y);
+    const int axis = (int)(packed & 3u);
+    const float split = na.x;
+    const float o_a = sel3(axis, r.ox, r.oy, r.oz);
+    const float d_a = sel3(axis, r.dx, r.dy, r.dz);
+    const float i_a = sel3(axis, T.ix, T.iy, T.iz);
+    const float t = (split - o_a) * i_a;
+    const bool below_first = (o_a < split) || (o_a == split && d_a <= 0.f);
+    const int pair = (int)(packed >> 2);
+    const int near_n = pair + (below_first ? 0 : 1);
+    const int far_n = pair + (below_first ? 1 : 0);
+    if (t > T.tmax || t <= 0.f) T.node = near_n;
+    else if (t < T.tmin) T.node = far_n;
+    else {
+        bool push = true;
+#ifndef WRT_PREPUSH
+#define WRT_PREPUSH 0   /* measured: no gain on C3, -1..2 % on torus / cbox (profiles/r1_experiments.md) */
+#endif
+        if (WRT_PREPUSH && T.res >= 0) {
+            const float4 fa = ldg4(&sc.nodes[2 * far_n]), fb = ldg4(&sc.nodes[2 * far_n + 1]);
+            push = !(bound_entry(fa, fb, r, T.ix, T.iy, T.iz) > T.best * WRT_PRUNE_REL);
+        }
+        if (push && T.sp < WRT_STACK_DEPTH) { S.e[T.sp] = make_float4(i2f(far_n), t, T.tmax, 0.f); ++T.sp; }
         T.node = near_n;
         T.tmax = t;
     }
@@ -202,7 +235,9 @@ WRT_HD void trav_leaf(const DevSceneView& sc, const float4 na, const RayIn& r, T
 WRT_HD bool trav_pop(Trav& T, const TravStack& S)
 {
     if (T.sp <= 0) return false;
-    --T.sp; T.node = S.node[T.sp]; T.tmin = S.tmin[T.sp]; T.tmax = S.tmax[T.sp];
+    --T.sp;
+    const float4 q = S.e[T.sp];
+    T.node = f2i(q.x); T.tmin = q.y; T.tmax = q.z;
     return true;
 }
 
@@ -219,7 +254,7 @@ WRT_HD int kd_traverse(const DevSceneView& sc, const RayIn& r, float& best_t, Vi
         if (!trav_skip<PRUNED>(sc, na, r, T)) {
             if ((f2u(na.y) & 3u) != WRT_LEAF_TAG) {
                 if (COUNT) vc->inner++;
-                trav_interior(na, r, T, S);
+                if (PRUNED) trav_interior_prune(sc, na, r, T, S); else trav_interior(na, r, T, S);
                 continue;
             }
             if (COUNT) vc->leaf++;

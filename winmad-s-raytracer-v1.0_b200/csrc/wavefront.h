@@ -52,6 +52,7 @@ struct wrt_wavefront {
     void* bdpt;                         // BDPT-only buffers (bdpt_wavefront.cu)
     size_t bdpt_bytes;
     cudaEvent_t* ev; int n_ev;          // stage-timing events (4 per iteration)
+    void* trav_scratch; size_t trav_scratch_bytes;   // pooled scheduler's traversal stacks for this sub-pool's launches
     cudaStream_t stream;                // this sub-pool's own stream (PT runs sub-pools concurrently)
     cudaEvent_t join_ev;
 };

@@ -4,7 +4,7 @@
 #pragma once
 #include "wavefront.h"
 #include "warp_utils.cuh"
-#include "trace_persistent.cuh"
+#include "trace_pooled.cuh"
 
 namespace wrt {
 
@@ -40,10 +40,11 @@ struct ExtendSrc {
 
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock)
-k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters)
+k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters,
+            float4* scratch)
 {
     ExtendSrc src = { pool, queue };
-    trace_rays<PRUNED>(sc, src, &counters[WF_WORK], n);
+    trace_rays<PRUNED>(sc, src, &counters[WF_WORK], n, scratch);
 }
 
 // Counting-mode variants: EXACT traversal with the reference-semantics visit counters.
@@ -117,11 +118,12 @@ struct ShadowSrc {
 
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock)
-k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters)
+k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters,
+            float4* scratch)
 {
     const size_t n = (size_t)counters[WF_SHADOW_COUNT];
     ShadowSrc src = { sq, film, scale };
-    trace_rays<PRUNED>(sc, src, &counters[WF_WORK3], n);
+    trace_rays<PRUNED>(sc, src, &counters[WF_WORK3], n, scratch);
 }
 
 }  // namespace wrt
