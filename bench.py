@@ -37,6 +37,10 @@ WORKLOADS = {
                   integrator="pt", width=512, height=512, spp=256, depth=7, fixture="torus"),
     "cbox_dragon": dict(desc="C2-class: Cornell walls + dragon (2,584 triangles), 512x512 PT, depth 7, 256 spp",
                         integrator="pt", width=512, height=512, spp=256, depth=7, fixture="cbox_dragon"),
+    "c5": dict(desc="C5: synthetic 10,008,338-triangle displaced torus + 100,000 spheres, 3840x2160 PT, depth 5, 16 spp per step (of 1024)",
+               integrator="pt", width=3840, height=2160, spp=16, depth=5, n=2237, n_spheres=100000),
+    "c5_small": dict(desc="C5 at 1/5 scale: 2,000,000-triangle displaced torus + 20,000 spheres, 3840x2160 PT, depth 5, 16 spp",
+                     integrator="pt", width=3840, height=2160, spp=16, depth=5, n=1000, n_spheres=20000),
     "c4": dict(desc="C4: closed Cornell box + area light, BDPT 1440x1440, 16 iterations per step (of 256), controlLength 3",
                integrator="bdpt", width=1440, height=1440, iterations=16, n=0),
 }
@@ -49,7 +53,7 @@ def make_scene(w):
         return sc
     if w["integrator"] == "bdpt":
         return scenes.cornell_box_scene(w["width"], w["height"], closed=True)
-    return scenes.synthetic_torus_scene(n=w["n"], width=w["width"], height=w["height"])
+    return scenes.synthetic_torus_scene(n=w["n"], width=w["width"], height=w["height"], n_spheres=w.get("n_spheres", 0))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -161,6 +165,19 @@ def run_reference(w, steps, warmup, nproc):
     return out, build_s
 
 
+def reference_procs(w):
+    """All the host threads the reference can use = independent processes, bounded by memory: the reference's
+    KD build keeps every node's event lists (about 2 GB per million primitives)."""
+    n = os.cpu_count() or 1
+    try:
+        import psutil
+        per_proc_gb = 0.5 + 2.2 * (w.get("n", 0) ** 2 * 2 / 1e6 if w.get("n") else 0.05)
+        n = min(n, max(1, int(psutil.virtual_memory().available / 2 ** 30 * 0.6 / per_proc_gb)))
+    except Exception:
+        n = min(n, 8)
+    return max(1, min(n, 64))
+
+
 def reference_workload(w):
     w = dict(w)
     if w["integrator"] == "pt":
@@ -201,7 +218,7 @@ def main():
         if not refpy.available():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libwrt_ref.so was not built (no /root/reference at build time)"}))
             return 0
-        nproc = os.cpu_count() or 1
+        nproc = reference_procs(w)
         rw = reference_workload(w)
         res, build_s = run_reference(rw, args.steps, max(args.warmup, 1), nproc)
         rays = sum(r[0] for r in res); samples = sum(r[1] for r in res); secs = sum(r[2] for r in res)

@@ -80,9 +80,10 @@ def synthetic_torus_scene(n=708, width=1920, height=1080, n_spheres=0, seed=1, n
     kind = np.zeros(len(data), np.int32)
     if n_spheres:
         rng = np.random.Generator(np.random.PCG64(seed))
-        lo, hi = np.array([-1.5, -1.5, floor_z]), np.array([1.5, 1.5, 0.6])
+        lo, hi = tris.reshape(-1, 3).min(0).astype(np.float64), tris.reshape(-1, 3).max(0).astype(np.float64)
         c = lo + (hi - lo) * rng.random((n_spheres, 3))
-        scene_r = 0.5 * np.linalg.norm([2 * f, 2 * f, 1.0])
+        ext = tris.reshape(-1, 3).max(0) - tris.reshape(-1, 3).min(0)
+        scene_r = 0.5 * float(np.linalg.norm(ext))             # radius of the mesh's bounding sphere (~2.0)
         rad = scene_r * 10 ** (-3 + rng.random(n_spheres))     # log-uniform in [1e-3, 1e-2] * scene radius
         sph = np.zeros((n_spheres, 9), np.float32)
         sph[:, :3] = c; sph[:, 3] = rad

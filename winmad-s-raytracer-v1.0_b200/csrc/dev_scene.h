@@ -50,6 +50,7 @@ struct DevSceneView {  // passed to kernels by value
     const DevMaterial* __restrict__ materials;
     const DevLight* __restrict__ lights;
     int n_nodes, n_prims, n_materials, n_lights;
+    int small_tree;          // < 512 nodes: rays are a handful of steps long, the plain per-thread loop wins
     float root_lo[3], root_hi[3];
     float sphere_center[3], sphere_radius, inv_sphere_radius_sqr;
 };

@@ -226,6 +226,7 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
     L.n_nodes = n_live; L.n_recs = n_recs;
     DevSceneView& v = L.view;
     memset(&v, 0, sizeof v);
+    v.small_tree = n_live < 512 ? 1 : 0;
     v.n_nodes = n_live; v.n_prims = d->n_prims; v.n_materials = d->n_materials; v.n_lights = d->n_lights;
     for (int a = 0; a < 3; a++) { v.root_lo[a] = T.root_box[a]; v.root_hi[a] = T.root_box[3 + a]; }
     {   // sceneSphere, scene.cpp:481-487

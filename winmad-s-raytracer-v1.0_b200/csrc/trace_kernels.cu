@@ -35,6 +35,7 @@ __device__ __forceinline__ bool visible_from(const RayIn& r, int prim, float t, 
 struct ClosestSrc {
     const DevSceneView* sc;
     const wrt_ray* rays; int32_t* prim; float* t_out; float* p3; float* n3; int32_t* inside; int32_t* matid;
+    __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
     __device__ __forceinline__ void done(size_t i, const RayIn& r, int id, float t) const
     {
@@ -63,6 +64,7 @@ k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int
 
 struct AnySrc {
     const wrt_ray* rays; uint8_t* hit;
+    __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
     __device__ __forceinline__ void done(size_t i, const RayIn&, int id, float) const { hit[i] = id >= 0 ? 1 : 0; }
 };
@@ -79,6 +81,7 @@ k_trace_any(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, uint8_t
 // shadowRayTest: ray given, target point given; visible = 1.0f / 0.0f
 struct ShadowTestSrc {
     const wrt_ray* rays; const float* target3; float* visible;
+    __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
     __device__ __forceinline__ void done(size_t i, const RayIn& r, int id, float t) const
     {
@@ -98,11 +101,21 @@ k_trace_shadow(DevSceneView sc, const wrt_ray* __restrict__ rays, const float* _
 // occluded(p1, dir, p2): builds Ray(p1, dir) (normalising dir) and negates shadowRayTest
 struct OccludedSrc {
     const float* q9; uint8_t* occluded;
-    __device__ __forceinline__ bool load(size_t i, RayIn& r) const
+    float tx, ty, tz;
+    __device__ __forceinline__ bool load(size_t i, RayIn& r)
     {
         const float* q = q9 + 9 * i;
         make_ray(q[0], q[1], q[2], q[3], q[4], q[5], r);
+        tx = q[6]; ty = q[7]; tz = q[8];
         return true;
+    }
+    // exact early exit, see ShadowSrc::decided (wavefront_kernels.cuh)
+    __device__ __forceinline__ bool decided(const RayIn& r, float best) const
+    {
+        const float m = 1.5f * WRT_EPS;
+        const float ex = (r.ox + r.dx * best) - tx, ey = (r.oy + r.dy * best) - ty, ez = (r.oz + r.dz * best) - tz;
+        return (r.dx > 0.f ? ex < -m : (r.dx < 0.f && ex > m)) || (r.dy > 0.f ? ey < -m : (r.dy < 0.f && ey > m)) ||
+               (r.dz > 0.f ? ez < -m : (r.dz < 0.f && ez > m));
     }
     __device__ __forceinline__ void done(size_t i, const RayIn& r, int id, float t) const
     {
@@ -116,7 +129,7 @@ __global__ void __launch_bounds__(kTraceBlock)
 k_trace_occluded(DevSceneView sc, const float* __restrict__ q9, size_t n, uint8_t* __restrict__ occluded,
                  unsigned long long* counter, float4* scratch)
 {
-    OccludedSrc src = { q9, occluded };
+    OccludedSrc src = { q9, occluded, 0.f, 0.f, 0.f };
     trace_rays<PRUNED>(sc, src, counter, n, scratch);
 }
 

@@ -206,10 +206,31 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
 #ifndef WRT_TRACE_SCHED
 #define WRT_TRACE_SCHED 2
 #endif
+// Scheduler 0: each warp pulls 32 consecutive work items and every lane runs kd_traverse() to completion.
+// No refill, no votes: cheapest bookkeeping, right for trees of a few dozen nodes (C4's Cornell box).
+template <bool PRUNED, class Src>
+__device__ __forceinline__ void trace_plain(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n)
+{
+    for (;;) {
+        unsigned long long b = 0;
+        if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 32ull);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n) break;
+        const size_t i = (size_t)b + (threadIdx.x & 31);
+        if (i >= n) continue;
+        RayIn r;
+        if (!src.load(i, r)) continue;
+        float t;
+        const int prim = kd_traverse<PRUNED, false>(sc, r, t, nullptr);
+        src.done(i, r, prim, t);
+    }
+}
+
 template <bool PRUNED, class Src>
 __device__ __forceinline__ void trace_rays(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n,
                                            float4* trav_scratch)
 {
+    if (sc.small_tree) { trace_plain<PRUNED>(sc, src, counter, n); return; }
 #if WRT_TRACE_SCHED == 3
     __shared__ PoolSmem pool_smem[4];                       // kernels launch 128 threads = 4 warps
     const unsigned warp = threadIdx.x >> 5;

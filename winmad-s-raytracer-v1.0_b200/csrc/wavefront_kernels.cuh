@@ -29,6 +29,7 @@ __device__ __forceinline__ void film_add(float* film, uint32_t pixel, V3 c, floa
 
 struct ExtendSrc {
     PathPool pool; const uint32_t* queue;
+    __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t e, RayIn& r) const { r = pool_load_ray(pool, queue[e]); return true; }
     __device__ __forceinline__ void done(size_t e, const RayIn&, int prim, float t) const
     {
@@ -98,11 +99,25 @@ k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, flo
 
 struct ShadowSrc {
     ShadowQueue sq; float* film; float scale;
-    __device__ __forceinline__ bool load(size_t e, RayIn& r) const
+    float tx, ty, tz;     // target point of the query this lane is tracing
+    __device__ __forceinline__ bool load(size_t e, RayIn& r)
     {
-        const float4 a = sq.a[e], b = sq.b[e];
+        const float4 a = sq.a[e], b = sq.b[e], c = sq.c[e];
         make_ray(a.x, a.y, a.z, b.x, b.y, b.z, r);
+        tx = c.x; ty = c.y; tz = c.z;
         return true;
+    }
+    // Scene::shadowRayTest only asks whether the closest hit point equals the target within EPS per
+    // component (scene.cpp:64-67).  `best` only decreases during the traversal, so once the current best hit
+    // lies BEFORE the target along some axis by clearly more than EPS, every later (smaller) best does too:
+    // the query is occluded whatever the rest of the traversal finds, and the lane can stop.  (A hit beyond
+    // the target decides nothing: a closer one may still move the hit point onto the target.)
+    __device__ __forceinline__ bool decided(const RayIn& r, float best) const
+    {
+        const float m = 1.5f * WRT_EPS;
+        const float ex = (r.ox + r.dx * best) - tx, ey = (r.oy + r.dy * best) - ty, ez = (r.oz + r.dz * best) - tz;
+        return (r.dx > 0.f ? ex < -m : (r.dx < 0.f && ex > m)) || (r.dy > 0.f ? ey < -m : (r.dy < 0.f && ey > m)) ||
+               (r.dz > 0.f ? ez < -m : (r.dz < 0.f && ez > m));
     }
     __device__ __forceinline__ void done(size_t e, const RayIn& r, int prim, float t) const
     {
@@ -122,7 +137,7 @@ k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float sca
             float4* scratch)
 {
     const size_t n = (size_t)counters[WF_SHADOW_COUNT];
-    ShadowSrc src = { sq, film, scale };
+    ShadowSrc src = { sq, film, scale, 0.f, 0.f, 0.f };
     trace_rays<PRUNED>(sc, src, &counters[WF_WORK3], n, scratch);
 }
 
