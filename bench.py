@@ -46,6 +46,11 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes per ray of k_pt_extend from the committed ncu capture (profiles/r1_final_launches_and_ncu.md):
+# (996.3 + 333.3) MB for one 8 388 608-ray launch on C3.
+NCU_DRAM_BYTES_PER_RAY = {"c3": (996.345088e6 + 333.309696e6) / 8388608.0}
+
+
 def make_scene(w):
     import scenes
     if "fixture" in w:
@@ -111,9 +116,10 @@ def _ref_worker(conn, w, rank, nproc):
         t0 = time.time()
         ref.build(sc.materials, sc.kind, sc.data, sc.matid, sc.lights, sc.cam12, sc.width, sc.height)
         conn.send(("ready", time.time() - t0))
-        cw, ch = w["crop"]
-        r0 = (sc.height - ch) // 2; c0 = (sc.width - cw) // 2
-        n_rows = len(range(r0 + rank, r0 + ch, nproc))    # interleaved rows: balanced work per process
+        stride = w["row_stride"]                              # every stride-th row of the whole frame
+        my_rows = range(rank * stride, sc.height, nproc * stride)
+        n_rows = len(my_rows)
+        cw = sc.width
         while True:
             msg = conn.recv()
             if msg == "stop":
@@ -122,8 +128,8 @@ def _ref_worker(conn, w, rank, nproc):
             t0 = time.perf_counter()
             if kind == "pt":
                 if n_rows:
-                    ref.render_pt_rows(1, w["depth"], 5489 + rank + 97 * msg, r0 + rank, r0 + ch, c0, c0 + cw,
-                                       want_film=False, row_stride=nproc)
+                    ref.render_pt_rows(1, w["depth"], 5489 + rank + 97 * msg, rank * stride, sc.height, 0, cw,
+                                       want_film=False, row_stride=nproc * stride)
                 samples = n_rows * cw
             else:
                 ref.render_bdpt(1, seed=5489 + rank + 97 * msg)
@@ -181,11 +187,11 @@ def reference_procs(w):
 def reference_workload(w):
     w = dict(w)
     if w["integrator"] == "pt":
-        # bounded sample: 1 spp on a centre crop of the same frame
-        w["crop"] = (512, 288) if w["width"] >= 1024 else (w["width"], w["height"] // 2)
+        # bounded sample: 1 spp on every k-th row of the whole frame (same ray mix as the full frame)
+        w["row_stride"] = 8 if w["width"] * w["height"] >= 2 ** 20 else 2
     else:
         w["width"] = w["height"] = 256   # BDPT must render whole (square) frames: 1 iteration at 256^2
-        w["crop"] = (256, 256)
+        w["row_stride"] = 1
     return w
 
 
@@ -223,8 +229,8 @@ def main():
         res, build_s = run_reference(rw, args.steps, max(args.warmup, 1), nproc)
         rays = sum(r[0] for r in res); samples = sum(r[1] for r in res); secs = sum(r[2] for r in res)
         v = rays / secs / 1e6
-        sample = ("1 spp on a %dx%d centre crop of the %dx%d frame per step, split by rows over %d independent reference processes"
-                  % (rw["crop"][0], rw["crop"][1], rw["width"], rw["height"], nproc))
+        sample = ("1 spp on every %d-th row of the %dx%d frame per step, rows dealt round-robin to %d independent reference processes"
+                  % (rw["row_stride"], rw["width"], rw["height"], nproc))
         line = {"metric": metric, "value": v, "unit": unit, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(len(res), 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -394,7 +400,10 @@ def main():
         line["roofline"] = {"bound": "hbm", "kernel": "k_pt_extend<pruned>", "achieved": achieved, "peak": peak,
                             "note": "launch durations are CUDA-event times of launches that overlap with the other sub-pool's kernels (2 streams), so this is a lower bound of the kernel's stand-alone rate",
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                            "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": (NCU_DRAM_BYTES_PER_RAY.get(args.workload) or 0) * ext_rays / max(ext_launches, 1) or None,
+                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per ray of one ncu --set full capture "
+                                              "(profiles/r1_final_launches_and_ncu.md) x rays per launch",
                             "bytes_per_ray": b_ray, "visits_per_ray_reference_semantics": visits,
                             "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
                             "rays_per_launch": ext_rays / max(ext_launches, 1),
@@ -421,14 +430,14 @@ def cpu_baseline(w, unit):
     if not refpy.available():
         return {"value": None, "unit": unit, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     rw = reference_workload(w)
-    if rw["integrator"] == "pt" and rw["width"] >= 1024:
-        rw["crop"] = (256, 144)
+    if rw["integrator"] == "pt":
+        rw["row_stride"] *= 2
     res, build_s = run_reference(rw, 1, 0, 1)
     rays, samples, secs = res[0]
     return {"value": rays / secs / 1e6, "unit": unit, "cores": 1, "kind": "reference",
-            "sample": "1 spp on a %dx%d centre crop of the %dx%d frame (%d rays, %.1f s); reference KD build %.1f s not timed"
-                      % (rw["crop"][0], rw["crop"][1], rw["width"], rw["height"], rays, secs, build_s),
-            "samples_per_s": samples / secs}
+            "sample": "1 spp on every %d-th row of the %dx%d frame (%d rays, %.1f s); reference KD build %.1f s not timed"
+                      % (rw["row_stride"], rw["width"], rw["height"], rays, secs, build_s),
+            "samples_per_s": samples / secs, "rays_per_sample": rays / max(samples, 1)}
 
 
 if __name__ == "__main__":
