@@ -20,12 +20,6 @@ namespace wrt {
 #define WRT_REFILL_THRESHOLD 28
 #endif
 constexpr int kRefillThreshold = WRT_REFILL_THRESHOLD;
-#ifndef WRT_RECORDS_PER_ROUND
-#define WRT_RECORDS_PER_ROUND 2
-#endif
-#ifndef WRT_NODES_PER_ROUND
-#define WRT_NODES_PER_ROUND 1
-#endif
 
 #ifndef WRT_FAST_DIV
 #define WRT_FAST_DIV 1
@@ -171,10 +165,11 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
                 if (active && in_leaf) {
                     // (loading both records up front was measured: 79 registers, 346 -> 281 Mrays/s)
                     const float best0 = T.best;
-#pragma unroll
-                    for (int s = 0; s < WRT_RECORDS_PER_ROUND; s++) {
+                    leaf_record(sc, rec, r, T);
+                    if (++rec == rec_end) { in_leaf = false; need_pop = true; }
+                    else {
                         leaf_record(sc, rec, r, T);
-                        if (++rec == rec_end) { in_leaf = false; need_pop = true; break; }
+                        if (++rec == rec_end) { in_leaf = false; need_pop = true; }
                     }
                     // boolean queries (Scene::occluded) may stop once the answer can no longer change
                     if (T.best < best0 && src.decided(r, T.best)) {
@@ -186,18 +181,19 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
                 // node round: (pop, then) one node visit per lane that is at a node
                 if (active && !in_leaf) {
                     bool finished = false;
-#pragma unroll
-                    for (int s = 0; s < WRT_NODES_PER_ROUND && !finished && !in_leaf; s++) {
-                        if (need_pop) { need_pop = false; finished = !trav_pop(T, S); if (finished) break; }
-                        if (r.tmax < T.tmin) { finished = true; break; }              // KDtreeAccel.cpp:323
-                        const float4 na = __ldg(&sc.nodes[2 * T.node]);
-                        if (trav_skip<PRUNED>(sc, na, r, T)) need_pop = true;
-                        else if ((__float_as_uint(na.y) & 3u) == WRT_LEAF_TAG) {
-                            const int cnt = (int)(__float_as_uint(na.y) >> 2);
-                            if (cnt > 0) { in_leaf = true; rec = __float_as_int(na.x); rec_end = rec + cnt; }
-                            else need_pop = true;
-                        } else if (PRUNED) trav_interior_prune(sc, na, r, T, S);
-                        else trav_interior(na, r, T, S);
+                    if (need_pop) { need_pop = false; finished = !trav_pop(T, S); }
+                    if (!finished) {
+                        if (r.tmax < T.tmin) finished = true;                      // KDtreeAccel.cpp:323
+                        else {
+                            const float4 na = __ldg(&sc.nodes[2 * T.node]);
+                            if (trav_skip<PRUNED>(sc, na, r, T)) need_pop = true;
+                            else if ((__float_as_uint(na.y) & 3u) == WRT_LEAF_TAG) {
+                                const int cnt = (int)(__float_as_uint(na.y) >> 2);
+                                if (cnt > 0) { in_leaf = true; rec = __float_as_int(na.x); rec_end = rec + cnt; }
+                                else need_pop = true;
+                            } else if (PRUNED) trav_interior_prune(sc, na, r, T, S);
+                            else trav_interior(na, r, T, S);
+                        }
                     }
                     if (finished) { src.done(item, r, T.res, (T.res >= 0) ? T.best : WRT_INF); active = false; }
                 }
