@@ -205,6 +205,12 @@ int wrt_render_bdpt(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params*
 int wrt_render_bdpt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p,
                         float* d_film_hw3, void* stream);
 
+/* ---- film resolve on the device ----------------------------------------------------- */
+/* The per-pixel pipeline of ImageFilm::outputImage (film.cpp:44-61, color.h:47-75): scale, clamp to [0,1],
+ * pow(1/gamma), (unsigned char)(c * 255.0).  d_film: H x W x 3 floats, d_rgb: H x W x 3 bytes (R,G,B). */
+int wrt_film_resolve_dev(const float* d_film_hw3, int32_t width, int32_t height, float scale, float gamma,
+                         uint8_t* d_rgb_hw3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,3 +142,21 @@ def test_bdpt_properties(wrt):
     s = scene.stats()
     with pytest.raises(wrt.WrtError):                                      # square films only, like the reference
         scene.render_bdpt(cam, wrt.BdptParams(res, res // 2, 1, 0, 10, 3, 4, 0, 1, 0.0, 0))
+
+
+def test_film_resolve_on_device(wrt, tmp_path):
+    """SURVEY §8(f)3: outputImage's pixel pipeline on the device == the host writer (ImageFilm::outputImage
+    restated in host/scene_io.cpp) up to one 8-bit level where powf differs by an ulp."""
+    import torch
+    rng = np.random.Generator(np.random.PCG64(2))
+    film = (rng.random((37, 53, 3)).astype(np.float32) ** 3) * 2.5 - 0.1      # includes <0 and >1
+    d_film = torch.from_numpy(film).cuda()
+    d_rgb = torch.zeros((37, 53, 3), dtype=torch.uint8, device="cuda")
+    wrt.film_resolve_dev(d_film.data_ptr(), 53, 37, 0.8, 2.2, d_rgb.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    p = str(tmp_path / "o.ppm")
+    wrt.film_write(p, film, 0.8, 2.2)
+    raw = open(p, "rb").read()
+    host = np.frombuffer(raw[len(b"P6\n53 37\n255\n"):], np.uint8).reshape(37, 53, 3).astype(np.int32)
+    dev = d_rgb.cpu().numpy().astype(np.int32)
+    assert np.abs(dev - host).max() <= 1 and (dev != host).mean() < 0.01

@@ -100,6 +100,30 @@ def test_exact_equals_pruned_large(wrt, name):
     assert total >= (1e7 if w > 512 else 4e6)
 
 
+def test_headline_scene_against_oracle_port(wrt):
+    """C3's own scene (1 002 528 triangles, reference-exact KD build on the host) against the oracle port on a
+    sample of primary, secondary and adversarial rays the port finishes in seconds."""
+    sc = scenes.synthetic_torus_scene(n=708, width=1920, height=1080)
+    port = engines.PortEngine(wrt, sc)
+    scene = wrt.Scene(port.hs)
+    cam = port.hs.camera()
+    rays = wrt.generate_rays(cam, scenes.pixel_centres(1920, 1080, step=12) + np.float32(0.37))
+    a = scene.intersect(rays, full=True); b = port.intersect(rays, full=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(util.bits(a[1]), util.bits(b[1]))
+    hit = a[0] >= 0
+    assert 0.2 < hit.mean() < 0.9
+    for k in (2, 3):
+        assert np.array_equal(util.bits(a[k][hit]), util.bits(b[k][hit]))
+    r2 = wrt.make_rays(scenes.bounce_rays(a[2], a[3], hit))
+    c, d = scene.intersect(r2), port.intersect(r2)
+    assert np.array_equal(c[0], d[0]) and np.array_equal(util.bits(c[1]), util.bits(d[1]))
+    q = scenes.nee_queries(a[2], hit, sc.lights)
+    assert np.array_equal(scene.occluded(q), port.occluded(q))
+    adv = wrt.make_rays(engines.adversarial_rays(sc, 6000))
+    e, f = scene.intersect(adv), port.intersect(adv)
+    assert np.array_equal(e[0], f[0]) and np.array_equal(util.bits(e[1]), util.bits(f[1]))
+
+
 def test_visit_counters_and_stats(wrt):
     sc, z = scenes.load_fixture("torus")
     cuda = engines.CudaEngine(wrt, sc, True); port = engines.PortEngine(wrt, sc)

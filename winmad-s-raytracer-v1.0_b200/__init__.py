@@ -94,7 +94,7 @@ EXPORTS = [
     "wrt_get_stats",
     "wrt_reset_stats", "wrt_trace_closest", "wrt_trace_closest_full", "wrt_trace_any", "wrt_trace_shadow",
     "wrt_trace_occluded", "wrt_trace_closest_dev", "wrt_trace_occluded_dev", "wrt_trace_count_visits",
-    "wrt_render_pt", "wrt_render_pt_dev", "wrt_render_bdpt", "wrt_render_bdpt_dev",
+    "wrt_render_pt", "wrt_render_pt_dev", "wrt_render_bdpt", "wrt_render_bdpt_dev", "wrt_film_resolve_dev",
 ]
 
 _lib = None
@@ -170,6 +170,12 @@ def film_write(path, film, scale=1.0, gamma=2.2):
     h, w = film.shape[0], film.shape[1]
     _check(lib().wrt_film_write(path.encode(), _ptr(film, _f32p), w, h, C.c_float(scale), C.c_float(gamma)),
            "wrt_film_write")
+
+
+def film_resolve_dev(d_film, width, height, scale, gamma, d_rgb, stream=None):
+    """ImageFilm::outputImage's scale/clamp/gamma/8-bit on device buffers (raw pointers)."""
+    _check(lib().wrt_film_resolve_dev(C.c_void_p(d_film), int(width), int(height), C.c_float(scale), C.c_float(gamma),
+                                      C.c_void_p(d_rgb), C.c_void_p(stream or 0)), "wrt_film_resolve_dev")
 
 
 class Parameters:

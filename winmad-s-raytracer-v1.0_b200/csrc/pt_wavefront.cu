@@ -54,7 +54,7 @@ k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0
 __global__ void __launch_bounds__(kBlock)
 k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in, size_t n,
            uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* counters,
-           unsigned long long* next_sample)
+           unsigned long long* next_sample, size_t n_gen_in, size_t cap)
 {
     size_t base;
     while (next_chunk(&counters[WF_WORK2], n, base)) {
@@ -64,7 +64,7 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
         RayIn r; PathData pd; ShadeOut out;
         out.alive = false; out.emit = false; out.shadow = false;
         if (valid) {
-            slot = queue_in[e];
+            slot = queue_slot(queue_in, e, n_gen_in, cap);
             r = pool_load_ray(pool, slot);
             pool_load_data(pool, slot, pd);
             pt_shade(sc, P, r, pd, pool.hit_prim[slot], pool.hit_t[slot], out);
@@ -79,18 +79,26 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
             sq.pixel[spos] = pd.pixel;
         }
         // path regeneration: a finished path's slot takes the next camera sample
-        bool alive = valid && out.alive;
+        const bool alive = valid && out.alive;
         const bool dead = valid && !out.alive;
         const unsigned long long snew = warp_append(next_sample, dead);
-        if (dead && snew < P.total_samples) {
-            pt_generate(P, cam, snew, r, pd);
-            alive = true;
-        }
+        const bool regen = dead && snew < P.total_samples;
+        if (regen) pt_generate(P, cam, snew, r, pd);
         const unsigned long long qpos = warp_append(&counters[WF_NEXT_COUNT], alive);
-        if (alive) {
-            pool_store(pool, slot, r, pd);
-            queue_out[qpos] = slot;
-        }
+        const unsigned long long gpos = warp_append(&counters[WF_WORK4], regen);
+        if (alive) { pool_store(pool, slot, r, pd); queue_out[qpos] = slot; }                 // continuing paths: front
+        if (regen) { pool_store(pool, slot, r, pd); queue_out[cap - 1 - gpos] = slot; }       // new camera rays: back
+    }
+}
+
+// ImageFilm::outputImage per pixel: scale, clamp, gamma, 8-bit (film.cpp:44-61, color.h:47-75)
+__global__ void k_film_resolve(const float* __restrict__ film, size_t n, float scale, float inv_gamma, uint8_t* __restrict__ out)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float c = film[i] * scale;
+        c = fminf(1.0f, fmaxf(c, 0.0f));
+        c = powf(c, inv_gamma);
+        out[i] = (unsigned char)((double)c * 255.0);
     }
 }
 
@@ -249,7 +257,7 @@ static void pt_plan(const PtParams& P, PtPlan& plan)
 }
 
 struct SubState {
-    wrt_wavefront* wf; size_t n; int cur; bool in_flight; int timed;
+    wrt_wavefront* wf; size_t n; size_t n_gen; int cur; bool in_flight; int timed;
 };
 
 static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st)
@@ -289,7 +297,7 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
         if (n0) k_pt_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first);
         WRT_CUDA(cudaGetLastError());
-        sub[j].n = n0; sub[j].cur = 0; sub[j].in_flight = false; sub[j].timed = 0;
+        sub[j].n = n0; sub[j].n_gen = 0; sub[j].cur = 0; sub[j].in_flight = false; sub[j].timed = 0;
         first += n0;
         sc->stats.kernel_launches += n0 ? 1 : 0;
     }
@@ -309,15 +317,15 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         const bool time_it = s.timed < kMaxTimed;
         if (time_it && 4 * (s.timed + 1) > wf->n_ev) { int r = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (r) return r; }
         cudaEvent_t* ev = time_it ? &wf->ev[4 * s.timed] : nullptr;
-        const size_t n = s.n; const int cur = s.cur;
+        const size_t n = s.n; const int cur = s.cur; const size_t ng = s.n_gen; const size_t cap = (size_t)wf->capacity;
         WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), q));
         if (ev) cudaEventRecord(ev[0], q);
-        if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
-        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
+        if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, ng, cap);
+        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch, ng, cap);
+        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch, ng, cap);
         if (ev) cudaEventRecord(ev[1], q);
         k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
-                                              d_film, wf->counters, next_sample);
+                                              d_film, wf->counters, next_sample, ng, cap);
         if (ev) cudaEventRecord(ev[2], q);
         if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
         else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
@@ -335,7 +343,8 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         sc->stats.extend_launches += 1; sc->stats.extend_rays += s.n;
         sc->stats.shadow_rays += wf->h_counters[WF_SHADOW_COUNT];
         sc->stats.kernel_launches += 3;
-        s.n = (size_t)wf->h_counters[WF_NEXT_COUNT];
+        s.n_gen = (size_t)wf->h_counters[WF_WORK4];
+        s.n = (size_t)wf->h_counters[WF_NEXT_COUNT] + s.n_gen;
         s.cur ^= 1;
         s.in_flight = false;
         return WRT_OK;
@@ -394,6 +403,17 @@ int wrt_render_pt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params*
     WRT_CUDA(cudaEventRecord(sc->ev1, st));
     WRT_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_render_ms = ms;
+    return WRT_OK;
+}
+
+int wrt_film_resolve_dev(const float* d_film, int32_t width, int32_t height, float scale, float gamma, uint8_t* d_rgb, void* stream)
+{
+    if (!d_film || !d_rgb || width <= 0 || height <= 0 || !(gamma > 0.f)) { set_error("wrt_film_resolve_dev: bad argument"); return WRT_ERR_INVALID; }
+    const size_t n = (size_t)width * height * 3;
+    const int block = 256;
+    const int grid = (int)std::min<size_t>((n + block - 1) / block, 148 * 8);
+    k_film_resolve<<<grid, block, 0, (cudaStream_t)stream>>>(d_film, n, scale, 1.f / gamma, d_rgb);
+    WRT_CUDA(cudaGetLastError());
     return WRT_OK;
 }
 

@@ -143,14 +143,48 @@ WRT_HD bool trav_begin(const DevSceneView& sc, const RayIn& r, Trav& T)
     return true;
 }
 
+// Entry AND exit distance of the ray through a conservative box (NaN slabs are ignored, i.e. never prune).
+WRT_HD void bound_interval(const float4 a, const float4 b, const RayIn& r, float ix, float iy, float iz, float& entry, float& exit_)
+{
+    float t0 = (a.z - r.ox) * ix, t1 = (b.y - r.ox) * ix;
+    bool nn = (t0 != t0 || t1 != t1);
+    const float ex = nn ? -HUGE_VALF : fminf(t0, t1), xx = nn ? HUGE_VALF : fmaxf(t0, t1);
+    t0 = (a.w - r.oy) * iy; t1 = (b.z - r.oy) * iy;
+    nn = (t0 != t0 || t1 != t1);
+    const float ey = nn ? -HUGE_VALF : fminf(t0, t1), xy = nn ? HUGE_VALF : fmaxf(t0, t1);
+    t0 = (b.x - r.oz) * iz; t1 = (b.w - r.oz) * iz;
+    nn = (t0 != t0 || t1 != t1);
+    const float ez = nn ? -HUGE_VALF : fminf(t0, t1), xz = nn ? HUGE_VALF : fmaxf(t0, t1);
+    entry = fmaxf(ex, fmaxf(ey, ez));
+    exit_ = fminf(xx, fminf(xy, xz));
+}
+
+#ifndef WRT_MISS_PRUNE
+#define WRT_MISS_PRUNE 1
+#endif
+
 template <bool PRUNED>
 WRT_HD bool trav_skip(const DevSceneView& sc, const float4 na, const RayIn& r, const Trav& T)
 {
+#if WRT_MISS_PRUNE
+    // Also skip a sub-tree whose conservative bounds the ray does not enter at all (or only behind its
+    // origin): a reported hit lies inside the bounds of its primitive, so nothing below can be hit.
+    if (PRUNED) {
+        const float4 nb = ldg4(&sc.nodes[2 * T.node + 1]);
+        float en, ex;
+        bound_interval(na, nb, r, T.ix, T.iy, T.iz, en, ex);
+        if (T.res >= 0 && en > T.best * WRT_PRUNE_REL) return true;
+        const float m = 1e-4f * (fabsf(en) + fabsf(ex)) + 1e-4f;
+        return (en > ex + m) || (ex < -m);
+    }
+    return false;
+#else
     if (PRUNED && T.res >= 0) {
         const float4 nb = ldg4(&sc.nodes[2 * T.node + 1]);
         return bound_entry(na, nb, r, T.ix, T.iy, T.iz) > T.best * WRT_PRUNE_REL;
     }
     return false;
+#endif
 }
 
 WRT_HD void trav_interior(const float4 na, const RayIn& r, Trav& T, TravStack& S)

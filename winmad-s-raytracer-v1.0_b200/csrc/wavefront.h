@@ -14,7 +14,7 @@ enum {
     WF_NEXT_COUNT = 3,  // entries appended to the next-bounce queue
     WF_SHADOW_COUNT = 4,
     WF_AUX_COUNT = 5,   // BDPT direct-illumination entries
-    WF_WORK4 = 6,
+    WF_WORK4 = 6,      // BDPT DI kernel work fetch; PT: regenerated camera rays appended from the back of the queue
     WF_AUX2_COUNT = 7,  // BDPT: BSDF-sampled rays traced by the DI kernel
     WF_PER_ITER = 8,    // counters [0, WF_PER_ITER) are zeroed before every iteration
     WF_NEXT_SAMPLE = 8, // next camera sample to hand out (path regeneration)

@@ -27,13 +27,22 @@ __device__ __forceinline__ void film_add(float* film, uint32_t pixel, V3 c, floa
     atomicAdd(&film[3 * (size_t)pixel + 2], c.z * scale);
 }
 
+// A queue holds two runs: regenerated camera rays, filled from the BACK of the array (work items
+// [0, n_gen)), then continuing paths, filled from the front (work items [n_gen, n_gen + n_cont)).  Camera rays of
+// consecutive samples are coherent (8x4 pixel tiles), bounce rays are not: keeping the two kinds in separate runs
+// keeps warps homogeneous.
+__device__ __forceinline__ uint32_t queue_slot(const uint32_t* queue, size_t e, size_t n_gen, size_t cap)
+{
+    return e < n_gen ? queue[cap - 1 - e] : queue[e - n_gen];
+}
+
 struct ExtendSrc {
-    PathPool pool; const uint32_t* queue;
+    PathPool pool; const uint32_t* queue; size_t n_gen, cap;
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
-    __device__ __forceinline__ bool load(size_t e, RayIn& r) const { r = pool_load_ray(pool, queue[e]); return true; }
+    __device__ __forceinline__ bool load(size_t e, RayIn& r) const { r = pool_load_ray(pool, queue_slot(queue, e, n_gen, cap)); return true; }
     __device__ __forceinline__ void done(size_t e, const RayIn&, int prim, float t) const
     {
-        const uint32_t slot = queue[e];
+        const uint32_t slot = queue_slot(queue, e, n_gen, cap);
         pool.hit_prim[slot] = prim;
         pool.hit_t[slot] = t;
     }
@@ -42,22 +51,23 @@ struct ExtendSrc {
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock)
 k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters,
-            float4* scratch)
+            float4* scratch, size_t n_gen = 0, size_t cap = 0)
 {
-    ExtendSrc src = { pool, queue };
+    ExtendSrc src = { pool, queue, n_gen, cap };
     trace_rays<PRUNED>(sc, src, &counters[WF_WORK], n, scratch);
 }
 
 // Counting-mode variants: EXACT traversal with the reference-semantics visit counters.
 static __global__ void __launch_bounds__(kBlock)
-k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters)
+k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters,
+                  size_t n_gen = 0, size_t cap = 0)
 {
     size_t base;
     unsigned long long a = 0, b = 0, c = 0, d = 0;
     while (next_chunk(&counters[WF_WORK], n, base)) {
         const size_t e = base + (threadIdx.x & 31);
         if (e >= n) continue;
-        const uint32_t slot = queue[e];
+        const uint32_t slot = queue_slot(queue, e, n_gen, cap);
         const RayIn r = pool_load_ray(pool, slot);
         VisitCounters vc = { 0u, 0u, 0u, 0u };
         float t;
