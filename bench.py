@@ -297,7 +297,7 @@ def main():
     host_film = host_film_t.numpy()
 
     # reference-semantics work per ray of THIS ray mix (1 spp / 1 iteration counting render): B_ray
-    b_ray, visits = None, None
+    b_ray, visits, b_ray_k, visits_k = None, None, None, None
     if rank == 0 and w["integrator"] == "pt":
         scene.set_counting(True); scene.reset_stats()
         scene.render_pt(cam, W.PtParams(w["width"], w["height"], 1, w["depth"], 7, 0, 1, 0.0), host_film)
@@ -305,6 +305,13 @@ def main():
         nr = float(s.closest_rays + s.shadow_rays)
         visits = {"inner": s.inner_visits / nr, "leaf": s.leaf_visits / nr, "tri": s.tri_tests / nr, "sphere": s.sphere_tests / nr}
         b_ray = 40 + 8 * visits["inner"] + 8 * visits["leaf"] + 40 * visits["tri"] + 20 * visits["sphere"]
+        # the same accounting for the PRUNED traversal the timed kernels run (their own work, 32-byte nodes, 48-byte records)
+        scene.set_counting(2); scene.reset_stats()
+        scene.render_pt(cam, W.PtParams(w["width"], w["height"], 1, w["depth"], 7, 0, 1, 0.0), host_film)
+        s = scene.stats(); scene.set_counting(False)
+        nr = float(s.closest_rays + s.shadow_rays)
+        visits_k = {"inner": s.inner_visits / nr, "leaf": s.leaf_visits / nr, "tri": s.tri_tests / nr, "sphere": s.sphere_tests / nr}
+        b_ray_k = 40 + 32 * (visits_k["inner"] + visits_k["leaf"]) + 48 * (visits_k["tri"] + visits_k["sphere"])
 
     def barrier():
         if dist is not None:
@@ -405,6 +412,10 @@ def main():
                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per ray of one ncu --set full capture "
                                               "(profiles/r1_final_launches_and_ncu.md) x rays per launch",
                             "bytes_per_ray": b_ray, "visits_per_ray_reference_semantics": visits,
+                            "kernel_own_work": {"visits_per_ray": visits_k, "bytes_per_ray": b_ray_k,
+                                                "achieved_GBps": (ext_rays * b_ray_k) / (ext_ms * 1e-3) / 1e9,
+                                                "note": "what the PRUNED kernels actually fetch (not counting skipped nodes): "
+                                                        "pruning removes most of the reference-semantics bytes, which is why frac can exceed 1"},
                             "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
                             "rays_per_launch": ext_rays / max(ext_launches, 1),
                             "kernel_share_of_step": ext_ms / ms,

@@ -163,8 +163,9 @@ int wrt_film_write(const char* path, const float* film_hw3, int32_t width, int32
 int wrt_scene_create(const wrt_scene_desc* desc, wrt_scene** out);
 void wrt_scene_destroy(wrt_scene* sc);
 int wrt_scene_set_traversal(wrt_scene* sc, int mode);  /* WRT_TRAVERSE_*; default PRUNED */
-/* Work accounting: when on, the integrators' trace kernels run the EXACT (reference-semantics)
- * traversal and add their per-ray visit counts to wrt_stats (inner_visits ... sphere_tests). */
+/* Work accounting: on = 1: the integrators' trace kernels run the EXACT (reference-semantics) traversal and
+ * add their per-ray visit counts to wrt_stats (inner_visits ... sphere_tests); on = 2: same counters for the
+ * PRUNED traversal, i.e. the work the production kernels really do. */
 int wrt_scene_set_counting(wrt_scene* sc, int on);
 int wrt_get_stats(wrt_scene* sc, wrt_stats* out);
 int wrt_reset_stats(wrt_scene* sc);

@@ -343,7 +343,7 @@ class Scene:
         _check(lib().wrt_scene_set_traversal(self._sc, int(mode)), "wrt_scene_set_traversal")
 
     def set_counting(self, on):
-        _check(lib().wrt_scene_set_counting(self._sc, int(bool(on))), "wrt_scene_set_counting")
+        _check(lib().wrt_scene_set_counting(self._sc, int(on)), "wrt_scene_set_counting")
 
     def stats(self):
         s = Stats()

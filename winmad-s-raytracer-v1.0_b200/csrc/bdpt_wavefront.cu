@@ -284,17 +284,18 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
     Bv.n_paths = B->n_paths;      // stride of the vertex array
     const bool pruned = sc->traversal_mode == WRT_TRAVERSE_PRUNED;
     const bool counting = sc->counting != 0;
+    const bool count_pruned = sc->counting == 2;
 
     static int g_li = persistent_grid_for((const void*)k_bdpt_light_init, kBlock);
     static int g_ci = persistent_grid_for((const void*)k_bdpt_camera_init, kBlock);
     static int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
     static int g_ext_e = persistent_grid_for((const void*)k_pt_extend<false>, kBlock);
-    static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count, kBlock);
+    static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count<false>, kBlock);
     static int g_ls = persistent_grid_for((const void*)k_bdpt_light_shade, kBlock);
     static int g_cs = persistent_grid_for((const void*)k_bdpt_camera_shade, kBlock);
     static int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
     static int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
-    static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count, kBlock);
+    static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count<false>, kBlock);
     static int g_di_p = persistent_grid_for((const void*)k_bdpt_di<true>, kBlock);
     static int g_di_e = persistent_grid_for((const void*)k_bdpt_di<false>, kBlock);
 
@@ -320,7 +321,8 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
                 cudaEvent_t* ev = time_it ? &wf->ev[4 * timed] : nullptr;
                 WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), st));
                 if (ev) cudaEventRecord(ev[0], st);
-                if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+                if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
+        else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
                 else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
                 else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
                 if (ev) cudaEventRecord(ev[1], st);
@@ -329,7 +331,8 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
                 else
                     k_bdpt_camera_shade<<<g_cs, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[cur], n, wf->queue[cur ^ 1], d_film, wf->counters);
                 if (ev) cudaEventRecord(ev[2], st);
-                if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
+                if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
+        else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
                 else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
                 else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
                 if (phase == 1) {

@@ -278,6 +278,7 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     }
     const bool pruned = sc->traversal_mode == WRT_TRAVERSE_PRUNED;
     const bool counting = sc->counting != 0;
+    const bool count_pruned = sc->counting == 2;
 
     static int g_init = persistent_grid_for((const void*)k_pt_init, kBlock);
     static int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
@@ -285,8 +286,8 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     static int g_shade = persistent_grid_for((const void*)k_pt_shade, kBlock);
     static int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
     static int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
-    static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count, kBlock);
-    static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count, kBlock);
+    static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count<false>, kBlock);
+    static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count<false>, kBlock);
 
     // initial fill: sub-pool j starts with samples [first, first + n0_j)
     unsigned long long first = 0;
@@ -320,14 +321,16 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         const size_t n = s.n; const int cur = s.cur; const size_t ng = s.n_gen; const size_t cap = (size_t)wf->capacity;
         WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), q));
         if (ev) cudaEventRecord(ev[0], q);
-        if (counting) k_pt_extend_count<<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, ng, cap);
+        if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, ng, cap);
+        else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, ng, cap);
         else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch, ng, cap);
         else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch, ng, cap);
         if (ev) cudaEventRecord(ev[1], q);
         k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
                                               d_film, wf->counters, next_sample, ng, cap);
         if (ev) cudaEventRecord(ev[2], q);
-        if (counting) k_pt_shadow_count<<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
+        else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
         else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
         else k_pt_shadow<false><<<g_sh_e, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
         if (ev) { cudaEventRecord(ev[3], q); s.timed++; }

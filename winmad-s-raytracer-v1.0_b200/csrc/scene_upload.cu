@@ -133,7 +133,7 @@ int wrt_scene_set_traversal(wrt_scene* sc, int mode)
 int wrt_scene_set_counting(wrt_scene* sc, int on)
 {
     if (!sc) { set_error("null scene"); return WRT_ERR_INVALID; }
-    sc->counting = on ? 1 : 0;
+    sc->counting = on == 2 ? 2 : (on ? 1 : 0);   // 1: EXACT (reference-semantics work), 2: PRUNED (this kernel's own work)
     return WRT_OK;
 }
 

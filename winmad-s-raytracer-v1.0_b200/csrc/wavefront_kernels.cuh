@@ -58,7 +58,8 @@ k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, 
 }
 
 // Counting-mode variants: EXACT traversal with the reference-semantics visit counters.
-static __global__ void __launch_bounds__(kBlock)
+template <bool PRUNED>
+__global__ void __launch_bounds__(kBlock)
 k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters,
                   size_t n_gen = 0, size_t cap = 0)
 {
@@ -71,7 +72,7 @@ k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ q
         const RayIn r = pool_load_ray(pool, slot);
         VisitCounters vc = { 0u, 0u, 0u, 0u };
         float t;
-        const int prim = kd_traverse<false, true>(sc, r, t, &vc);
+        const int prim = kd_traverse<PRUNED, true>(sc, r, t, &vc);
         pool.hit_prim[slot] = prim;
         pool.hit_t[slot] = t;
         a += vc.inner; b += vc.leaf; c += vc.tri; d += vc.sph;
@@ -80,7 +81,8 @@ k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ q
     atomicAdd(&counters[WF_VISITS + 2], c); atomicAdd(&counters[WF_VISITS + 3], d);
 }
 
-static __global__ void __launch_bounds__(kBlock)
+template <bool PRUNED>
+__global__ void __launch_bounds__(kBlock)
 k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters)
 {
     const size_t n = (size_t)counters[WF_SHADOW_COUNT];
@@ -94,7 +96,7 @@ k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, flo
         make_ray(qa.x, qa.y, qa.z, qb.x, qb.y, qb.z, r);
         VisitCounters vc = { 0u, 0u, 0u, 0u };
         float t;
-        const int prim = kd_traverse<false, true>(sc, r, t, &vc);
+        const int prim = kd_traverse<PRUNED, true>(sc, r, t, &vc);
         a += vc.inner; b += vc.leaf; c += vc.tri; d += vc.sph;
         bool vis = prim < 0;
         if (!vis) {
