@@ -4,9 +4,9 @@
 // kRefillThreshold lanes are still traversing, the idle lanes claim the next work items from a global
 // counter (one atomicAdd per refill, ballot/popc ranks) and start new rays while the busy lanes keep
 // theirs.  Rays in this tree differ by two orders of magnitude in length (SIMT efficiency without
-// refill: ~3 of 32 lanes, profiles/r1_ncu_extend_summary.md), so this is the main lever.
-// Inside the work loop the warp alternates between "every busy lane walks down to its next leaf" and
-// "every busy lane intersects its leaf" (while-while), so both phases run converged.
+// refill: ~3 of 32 lanes, profiles/r1_ncu_extend_v0_summary.md).
+// Inside the work loop every busy lane is either at a node or inside a leaf, and each round the warp
+// votes which of the two code paths to run (trace_persistent_vote below).
 //
 // `Src` supplies the work:  bool load(size_t item, RayIn& r)  — build the ray of work item `item`
 //                           void done(size_t item, const RayIn& r, int prim, float t) — consume the result

@@ -18,9 +18,18 @@ namespace wrt {
 
 constexpr int kPoolRays = 64;          // rays per warp (power of two)
 constexpr int kPoolStack = 32;         // stack entries per ray (reference: depMax + 5, <= 29 for 1e8 primitives)
-constexpr int kNodeSteps = 2;
-constexpr int kPrimSteps = 2;
-constexpr unsigned kMinRefill = 16;
+#ifndef WRT_POOL_NODE_STEPS
+#define WRT_POOL_NODE_STEPS 2
+#endif
+#ifndef WRT_POOL_PRIM_STEPS
+#define WRT_POOL_PRIM_STEPS 2
+#endif
+#ifndef WRT_POOL_MIN_REFILL
+#define WRT_POOL_MIN_REFILL 16
+#endif
+constexpr int kNodeSteps = WRT_POOL_NODE_STEPS;
+constexpr int kPrimSteps = WRT_POOL_PRIM_STEPS;
+constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 
 struct PoolSmem {
     float4 a[kPoolRays];               // ox oy oz dx
@@ -202,7 +211,8 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
 }
 
 // Compile-time choice of the scheduler used by the kernels (A/B measured in profiles/):
-// 1 = lane refill + while-while, 2 = lane refill + vote (default: fastest measured, profiles/), 3 = pooled.
+// 2 = lane refill + vote, 3 = pooled.  (Scheduler 1, lane refill + while-while, was measured and removed:
+// profiles/r1_ncu_extend_schedulers.md.)
 #ifndef WRT_TRACE_SCHED
 #define WRT_TRACE_SCHED 2
 #endif
@@ -236,10 +246,8 @@ __device__ __forceinline__ void trace_rays(const DevSceneView& sc, Src& src, uns
     const unsigned warp = threadIdx.x >> 5;
     float4* stk = trav_scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * ((size_t)kPoolStack * kPoolRays);
     trace_pooled<PRUNED>(sc, src, counter, n, pool_smem[warp], stk);
-#elif WRT_TRACE_SCHED == 2
-    trace_persistent_vote<PRUNED>(sc, src, counter, n);
 #else
-    trace_persistent<PRUNED>(sc, src, counter, n);
+    trace_persistent_vote<PRUNED>(sc, src, counter, n);
 #endif
 }
 
