@@ -25,6 +25,17 @@ static void cam_fill(const wrt_camera* c, DevCamera& d)
     memcpy(d.w2r, c->world_to_raster, sizeof d.w2r);
 }
 
+
+static inline int hs_traverse(const DevSceneView& sc, const RayIn& r, int pruned, float& t)
+{
+    return pruned ? kd_traverse<true, false>(sc, r, t, nullptr) : kd_traverse<false, false>(sc, r, t, nullptr);
+}
+
+static inline bool hs_visible(const DevSceneView& sc, const RayIn& r, int pruned, float px, float py, float pz)
+{
+    return pruned ? shadow_visible<true>(sc, r, px, py, pz) : shadow_visible<false>(sc, r, px, py, pz);
+}
+
 extern "C" {
 
 int hs_scene_create(const wrt_scene_desc* d, void** out, char* err256)
@@ -48,7 +59,7 @@ void hs_trace_closest(void* hv, const wrt_ray* rays, size_t n, int pruned, int32
     for (size_t i = 0; i < n; i++) {
         RayIn r = { rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz, rays[i].tmin, rays[i].tmax };
         float tt;
-        prim[i] = pruned ? kd_traverse<true, false>(sc, r, tt, nullptr) : kd_traverse<false, false>(sc, r, tt, nullptr);
+        prim[i] = hs_traverse(sc, r, pruned, tt);
         if (t) t[i] = tt;
     }
 }
@@ -60,7 +71,7 @@ void hs_trace_closest_full(void* hv, const wrt_ray* rays, size_t n, int pruned, 
     for (size_t i = 0; i < n; i++) {
         RayIn r = { rays[i].ox, rays[i].oy, rays[i].oz, rays[i].dx, rays[i].dy, rays[i].dz, rays[i].tmin, rays[i].tmax };
         float tt;
-        int id = pruned ? kd_traverse<true, false>(sc, r, tt, nullptr) : kd_traverse<false, false>(sc, r, tt, nullptr);
+        int id = hs_traverse(sc, r, pruned, tt);
         prim[i] = id; t[i] = tt;
         HitInfo h = { 0, 0, 0, 0, 0, 0, 0, 0 };
         if (id >= 0) fill_hit(sc, id, r, tt, h);
@@ -77,7 +88,7 @@ void hs_trace_occluded(void* hv, const float* q9, size_t n, int pruned, uint8_t*
         const float* q = q9 + 9 * i;
         RayIn r;
         make_ray(q[0], q[1], q[2], q[3], q[4], q[5], r);
-        bool vis = pruned ? shadow_visible<true>(sc, r, q[6], q[7], q[8]) : shadow_visible<false>(sc, r, q[6], q[7], q[8]);
+        bool vis = hs_visible(sc, r, pruned, q[6], q[7], q[8]);
         occ[i] = vis ? 0 : 1;
     }
 }
@@ -127,7 +138,7 @@ void hs_render_pt(void* hv, const wrt_camera* cam, const wrt_pt_params* p, int p
         pt_generate(P, dc, s, r, pd);
         for (;;) {
             float t;
-            int prim = pruned ? kd_traverse<true, false>(sc, r, t, nullptr) : kd_traverse<false, false>(sc, r, t, nullptr);
+            int prim = hs_traverse(sc, r, pruned, t);
             nrays++;
             ShadeOut out;
             pt_shade(sc, P, r, pd, prim, t, out);
@@ -137,7 +148,7 @@ void hs_render_pt(void* hv, const wrt_camera* cam, const wrt_pt_params* p, int p
                 RayIn sr;
                 make_ray(out.q[0], out.q[1], out.q[2], out.q[3], out.q[4], out.q[5], sr);
                 nrays++;
-                bool vis = pruned ? shadow_visible<true>(sc, sr, out.q[6], out.q[7], out.q[8]) : shadow_visible<false>(sc, sr, out.q[6], out.q[7], out.q[8]);
+                bool vis = hs_visible(sc, sr, pruned, out.q[6], out.q[7], out.q[8]);
                 if (vis) { px[0] += out.shadow_c.x * P.film_scale; px[1] += out.shadow_c.y * P.film_scale; px[2] += out.shadow_c.z * P.film_scale; }
             }
             if (!out.alive) break;

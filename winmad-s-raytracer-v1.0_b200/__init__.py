@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwrt_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("WRT_B200_LIB", "libwrt_b200.so"))   # override: A/B builds made by tools/build_variant.sh
 
 OK = 0
 TRAVERSE_EXACT, TRAVERSE_PRUNED = 0, 1

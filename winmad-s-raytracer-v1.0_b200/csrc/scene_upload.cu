@@ -85,7 +85,14 @@ int wrt_scene_create(const wrt_scene_desc* d, wrt_scene** out)
         cudaError_t e__ = cudaMalloc(&(dst), bytes__); \
         if (e__ == cudaSuccess && !(vec).empty()) e__ = cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof(T_), cudaMemcpyHostToDevice); \
         if (e__ != cudaSuccess) { int rc__ = cuda_fail(e__, "scene upload"); wrt_scene_destroy(sc); return rc__; } } while (0)
-    UP(sc->d_nodes, nodes, float4);
+    {   // The root is node 0 and sibling pairs start at odd indices (breadth-first layout).  Placing node 0 at
+        // byte 32 of the allocation makes every child pair one aligned 64-byte read (pair_traverse.cuh).
+        const size_t bytes = (nodes.size() + 2) * sizeof(float4);
+        cudaError_t e = cudaMalloc(&sc->d_nodes, bytes);
+        if (e == cudaSuccess) e = cudaMemset(sc->d_nodes, 0, 2 * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMemcpy((float4*)sc->d_nodes + 2, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { int rc = cuda_fail(e, "scene upload"); wrt_scene_destroy(sc); return rc; }
+    }
     UP(sc->d_leaf_recs, recs, float4);
     UP(sc->d_prims, prims, float4);
     UP(sc->d_materials, mats, DevMaterial);
@@ -102,7 +109,7 @@ int wrt_scene_create(const wrt_scene_desc* d, wrt_scene** out)
     }
     sc->view = L.view;
     DevSceneView& v = sc->view;
-    v.nodes = (const float4*)sc->d_nodes; v.leaf_recs = (const float4*)sc->d_leaf_recs;
+    v.nodes = (const float4*)sc->d_nodes + 2; v.leaf_recs = (const float4*)sc->d_leaf_recs;
     v.prims = (const float4*)sc->d_prims;
     v.materials = (const DevMaterial*)sc->d_materials; v.lights = (const DevLight*)sc->d_lights;
     *out = sc;

@@ -35,6 +35,8 @@ __device__ __forceinline__ bool visible_from(const RayIn& r, int prim, float t, 
 struct ClosestSrc {
     const DevSceneView* sc;
     const wrt_ray* rays; int32_t* prim; float* t_out; float* p3; float* n3; int32_t* inside; int32_t* matid;
+    static constexpr bool kCanDecide = false;
+    __device__ __forceinline__ void target(size_t, float&, float&, float&) const {}
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
     __device__ __forceinline__ void done(size_t i, const RayIn& r, int id, float t) const
@@ -64,6 +66,8 @@ k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int
 
 struct AnySrc {
     const wrt_ray* rays; uint8_t* hit;
+    static constexpr bool kCanDecide = false;
+    __device__ __forceinline__ void target(size_t, float&, float&, float&) const {}
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
     __device__ __forceinline__ void done(size_t i, const RayIn&, int id, float) const { hit[i] = id >= 0 ? 1 : 0; }
@@ -81,6 +85,8 @@ k_trace_any(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, uint8_t
 // shadowRayTest: ray given, target point given; visible = 1.0f / 0.0f
 struct ShadowTestSrc {
     const wrt_ray* rays; const float* target3; float* visible;
+    static constexpr bool kCanDecide = true;      // scheduler 4: stop once the verdict can no longer change (occlusion_decided)
+    __device__ __forceinline__ void target(size_t i, float& x, float& y, float& z) const { x = target3[3 * i]; y = target3[3 * i + 1]; z = target3[3 * i + 2]; }
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
     __device__ __forceinline__ void done(size_t i, const RayIn& r, int id, float t) const
@@ -102,6 +108,8 @@ k_trace_shadow(DevSceneView sc, const wrt_ray* __restrict__ rays, const float* _
 struct OccludedSrc {
     const float* q9; uint8_t* occluded;
     float tx, ty, tz;
+    static constexpr bool kCanDecide = true;
+    __device__ __forceinline__ void target(size_t i, float& x, float& y, float& z) const { x = q9[9 * i + 6]; y = q9[9 * i + 7]; z = q9[9 * i + 8]; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r)
     {
         const float* q = q9 + 9 * i;
@@ -170,10 +178,10 @@ int persistent_grid_for(const void* kernel, int block)
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#if WRT_TRACE_SCHED != 3
-    // traversal is bound by L1TEX: give the kernels the whole unified cache as L1
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-#endif
+    // traversal is bound by L1TEX: kernels that keep no state in shared memory get the whole unified cache as L1
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess && fa.sharedSizeBytes == 0)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > kMaxBlocksPerSm) per_sm = kMaxBlocksPerSm;   // the traversal scratch is sized for this many

@@ -80,8 +80,21 @@ __device__ __forceinline__ bool triangle_wins(float p0x, float p0y, float p0z, f
     return true;
 }
 
+// Scene::occluded / shadowRayTest only ask whether the closest hit point equals the target within EPS per
+// component (scene.cpp:64-67).  `best` only decreases during a traversal, so once the current best hit lies
+// BEFORE the target along some axis by clearly more than EPS, every later (smaller) best does too.
+__device__ __forceinline__ bool occlusion_decided(const RayIn& r, float best, float tx, float ty, float tz)
+{
+    const float m = 1.5f * WRT_EPS;
+    const float ex = (r.ox + r.dx * best) - tx, ey = (r.oy + r.dy * best) - ty, ez = (r.oz + r.dz * best) - tz;
+    return (r.dx > 0.f ? ex < -m : (r.dx < 0.f && ex > m)) || (r.dy > 0.f ? ey < -m : (r.dy < 0.f && ey > m)) ||
+           (r.dz > 0.f ? ez < -m : (r.dz < 0.f && ez > m));
+}
+
 // One leaf record against the ray + the reference's acceptance rule (KDtreeAccel.cpp:363-373).
-__device__ __forceinline__ void leaf_record_regs(const float4 r0, const float4 r1, const float4 r2, const RayIn& r, Trav& T)
+// (TT: any traversal state with `best` and `res`.)
+template <class TT>
+__device__ __forceinline__ void leaf_record_regs(const float4 r0, const float4 r1, const float4 r2, const RayIn& r, TT& T)
 {
     if (__float_as_int(r2.w) == 0) {
         float t;
@@ -93,7 +106,8 @@ __device__ __forceinline__ void leaf_record_regs(const float4 r0, const float4 r
     }
 }
 
-__device__ __forceinline__ void leaf_record(const DevSceneView& sc, int rec_index, const RayIn& r, Trav& T)
+template <class TT>
+__device__ __forceinline__ void leaf_record(const DevSceneView& sc, int rec_index, const RayIn& r, TT& T)
 {
     const float4* rec = sc.leaf_recs + 3 * (size_t)rec_index;
     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
@@ -102,7 +116,8 @@ __device__ __forceinline__ void leaf_record(const DevSceneView& sc, int rec_inde
 
 // Two consecutive records of one leaf: all six loads are issued before the first test so the second
 // record's latency hides behind the first record's arithmetic (the records are adjacent: 96 bytes).
-__device__ __forceinline__ void leaf_record_pair(const DevSceneView& sc, int rec_index, const RayIn& r, Trav& T)
+template <class TT>
+__device__ __forceinline__ void leaf_record_pair(const DevSceneView& sc, int rec_index, const RayIn& r, TT& T)
 {
     const float4* rec = sc.leaf_recs + 3 * (size_t)rec_index;
     const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1), a2 = __ldg(rec + 2);

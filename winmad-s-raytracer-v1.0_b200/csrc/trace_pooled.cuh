@@ -16,16 +16,19 @@
 
 namespace wrt {
 
-constexpr int kPoolRays = 64;          // rays per warp (power of two)
+#ifndef WRT_POOL_RAYS
+#define WRT_POOL_RAYS 64
+#endif
+constexpr int kPoolRays = WRT_POOL_RAYS;   // rays per warp (power of two, <= 256)
 constexpr int kPoolStack = 32;         // stack entries per ray (reference: depMax + 5, <= 29 for 1e8 primitives)
 #ifndef WRT_POOL_NODE_STEPS
-#define WRT_POOL_NODE_STEPS 2
+#define WRT_POOL_NODE_STEPS 6
 #endif
 #ifndef WRT_POOL_PRIM_STEPS
-#define WRT_POOL_PRIM_STEPS 2
+#define WRT_POOL_PRIM_STEPS 4
 #endif
 #ifndef WRT_POOL_MIN_REFILL
-#define WRT_POOL_MIN_REFILL 16
+#define WRT_POOL_MIN_REFILL 32
 #endif
 constexpr int kNodeSteps = WRT_POOL_NODE_STEPS;
 constexpr int kPrimSteps = WRT_POOL_PRIM_STEPS;
@@ -108,7 +111,7 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
             if (have) slot = sm.ring[1][(hp + lane) & RM];
             hp += cnt;
             __syncwarp();
-            bool leaf_done = false;
+            bool leaf_done = false, decided = false;
             if (have) {
                 const float4 a = sm.a[slot], b = sm.b[slot];
                 RayIn r; r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
@@ -120,17 +123,30 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                     leaf_record(sc, e.y, r, T);
                     if (++e.y == e.z) { leaf_done = true; break; }
                 }
-                if (T.best != best0) { sm.c[slot].w = T.best; }
-                e.x = T.res;
-                sm.e[slot] = e;
-                if (leaf_done) sm.d[slot].w = __int_as_float(__float_as_int(sm.d[slot].w) | (1 << 30));   // need_pop
+                // boolean queries (Scene::occluded) stop once the answer can no longer change (occlusion_decided)
+                if (Src::kCanDecide && T.best < best0) {
+                    float tx, ty, tz;
+                    src.target((size_t)(unsigned)e.w, tx, ty, tz);
+                    if (occlusion_decided(r, T.best, tx, ty, tz)) { src.done((size_t)(unsigned)e.w, r, T.res, T.best); decided = true; }
+                }
+                if (!decided) {
+                    if (T.best != best0) { sm.c[slot].w = T.best; }
+                    e.x = T.res;
+                    sm.e[slot] = e;
+                    if (leaf_done) sm.d[slot].w = __int_as_float(__float_as_int(sm.d[slot].w) | (1 << 30));   // need_pop
+                }
             }
-            const unsigned b1 = __ballot_sync(FULL, have && !leaf_done);
-            if (have && !leaf_done) sm.ring[1][(tp + __popc(b1 & lt)) & RM] = (unsigned char)slot;
+            const unsigned b1 = __ballot_sync(FULL, have && !leaf_done && !decided);
+            if (have && !leaf_done && !decided) sm.ring[1][(tp + __popc(b1 & lt)) & RM] = (unsigned char)slot;
             tp += __popc(b1);
-            const unsigned b0 = __ballot_sync(FULL, have && leaf_done);
-            if (have && leaf_done) sm.ring[0][(tn + __popc(b0 & lt)) & RM] = (unsigned char)slot;
+            const unsigned b0 = __ballot_sync(FULL, have && leaf_done && !decided);
+            if (have && leaf_done && !decided) sm.ring[0][(tn + __popc(b0 & lt)) & RM] = (unsigned char)slot;
             tn += __popc(b0);
+            if (Src::kCanDecide) {
+                const unsigned b2 = __ballot_sync(FULL, decided);
+                if (decided) sm.ring[2][(tf + __popc(b2 & lt)) & RM] = (unsigned char)slot;
+                tf += __popc(b2);
+            }
             __syncwarp();
         } else {
             // ---- node round ---------------------------------------------------------------------
@@ -211,10 +227,12 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
 }
 
 // Compile-time choice of the scheduler used by the kernels (A/B measured in profiles/):
-// 2 = lane refill + vote, 3 = pooled.  (Scheduler 1, lane refill + while-while, was measured and removed:
+// 2 = lane refill + vote, 3 = pooled (default).  Measured and removed (profiles/r1_experiments.md, "Schedulers 4 and 5"):
+// scheduler 1 (lane refill + while-while), scheduler 4 (pooled + child-pair node visits: both children fetched and
+// bounds-tested at the parent) and scheduler 5 (k rays owned by every lane, state in conflict-free shared memory).  (Scheduler 1, lane refill + while-while, was measured and removed:
 // profiles/r1_ncu_extend_schedulers.md.)
 #ifndef WRT_TRACE_SCHED
-#define WRT_TRACE_SCHED 2
+#define WRT_TRACE_SCHED 3
 #endif
 // Scheduler 0: each warp pulls 32 consecutive work items and every lane runs kd_traverse() to completion.
 // No refill, no votes: cheapest bookkeeping, right for trees of a few dozen nodes (C4's Cornell box).

@@ -9,6 +9,9 @@
 namespace wrt {
 
 constexpr int kBlock = 128;
+#ifndef WRT_MIN_BLOCKS
+#define WRT_MIN_BLOCKS 1               /* __launch_bounds__ second argument of the traversal kernels (register cap) */
+#endif
 
 __device__ __forceinline__ RayIn pool_load_ray(const PathPool& pool, uint32_t slot)
 {
@@ -38,6 +41,8 @@ __device__ __forceinline__ uint32_t queue_slot(const uint32_t* queue, size_t e, 
 
 struct ExtendSrc {
     PathPool pool; const uint32_t* queue; size_t n_gen, cap;
+    static constexpr bool kCanDecide = false;
+    __device__ __forceinline__ void target(size_t, float&, float&, float&) const {}
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t e, RayIn& r) const { r = pool_load_ray(pool, queue_slot(queue, e, n_gen, cap)); return true; }
     __device__ __forceinline__ void done(size_t e, const RayIn&, int prim, float t) const
@@ -49,7 +54,7 @@ struct ExtendSrc {
 };
 
 template <bool PRUNED>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, WRT_MIN_BLOCKS)
 k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters,
             float4* scratch, size_t n_gen = 0, size_t cap = 0)
 {
@@ -111,7 +116,9 @@ k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, flo
 
 struct ShadowSrc {
     ShadowQueue sq; float* film; float scale;
-    float tx, ty, tz;     // target point of the query this lane is tracing
+    float tx, ty, tz;     // target point of the query this lane is tracing (scheduler 2: one ray per lane)
+    static constexpr bool kCanDecide = true;
+    __device__ __forceinline__ void target(size_t e, float& x, float& y, float& z) const { const float4 c = sq.c[e]; x = c.x; y = c.y; z = c.z; }
     __device__ __forceinline__ bool load(size_t e, RayIn& r)
     {
         const float4 a = sq.a[e], b = sq.b[e], c = sq.c[e];
@@ -144,7 +151,7 @@ struct ShadowSrc {
 };
 
 template <bool PRUNED>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, WRT_MIN_BLOCKS)
 k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters,
             float4* scratch)
 {
