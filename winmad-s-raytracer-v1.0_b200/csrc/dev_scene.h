@@ -11,6 +11,7 @@ namespace wrt {
 #define WRT_INF 1e7f
 #define WRT_STACK_DEPTH 40      /* reference: depMax + 5 = (int)(1.2 ln N + 2) + 5; 29 at N = 1e8 */
 #define WRT_LEAF_TAG 3u
+#define WRT_REC_SKIP 2          /* leaf record kind: conservative box of the next n records (kinds 0 / 1: triangle / sphere) */
 
 // KD node, 32 bytes = one L2 sector, two 16-byte loads:
 //   a.x  split plane (interior)            | first leaf record (leaf), as int bits
@@ -25,6 +26,9 @@ struct DevNodeHalf { float x, y, z, w; };
 // primitives are contiguous:
 //   triangle: r0 = p0.xyz, prim id   r1 = p0-p1 (A,B,C), 0      r2 = p0-p2 (D,E,F), kind=0
 //   sphere:   r0 = c.xyz,  prim id   r1 = radius, box.l.xyz     r2 = box.r.xyz,     kind=1
+//   skip:     r0 = lo.xyz, n         r1 = hi.xyz, 0             r2 = 0, 0, 0,       kind=2
+// A skip record holds the conservative box of the n records that follow it (primitive records of consecutive list
+// entries, possibly with nested skip records): PRUNED traversal jumps over them when the box is prunable.
 // (p0-p1 and p0-p2 are the same float subtractions Triangle::hit performs first, triangle.cpp:24-30.)
 
 struct DevMaterial {  // Material, R/src/material/material.h:7-31

@@ -92,10 +92,15 @@ __device__ __forceinline__ bool occlusion_decided(const RayIn& r, float best, fl
 }
 
 // One leaf record against the ray + the reference's acceptance rule (KDtreeAccel.cpp:363-373).
-// (TT: any traversal state with `best` and `res`.)
-template <class TT>
-__device__ __forceinline__ void leaf_record_regs(const float4 r0, const float4 r1, const float4 r2, const RayIn& r, TT& T)
+// Returns how many records to advance: 1, or 1 + n for a prunable skip record (PRUNED only).
+// (TT: any traversal state with `best`, `res` and invDir `ix, iy, iz`.)
+template <bool PRUNED, class TT>
+__device__ __forceinline__ int leaf_record_regs(const float4 r0, const float4 r1, const float4 r2, const RayIn& r, TT& T)
 {
+    if (__float_as_int(r2.w) == WRT_REC_SKIP) {
+        if (PRUNED && box_prunable(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r, T.ix, T.iy, T.iz, T.res, T.best)) return 1 + __float_as_int(r0.w);
+        return 1;
+    }
     if (__float_as_int(r2.w) == 0) {
         float t;
         if (triangle_wins(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, T.best, t)) { T.best = t; T.res = __float_as_int(r0.w); }
@@ -104,26 +109,15 @@ __device__ __forceinline__ void leaf_record_regs(const float4 r0, const float4 r
         int inside; float t;
         if (sphere_t(r0.x, r0.y, r0.z, r1.x, lo, hi, r, t, inside) && (t - T.best < -WRT_EPS)) { T.best = t; T.res = __float_as_int(r0.w); }
     }
+    return 1;
 }
 
-template <class TT>
-__device__ __forceinline__ void leaf_record(const DevSceneView& sc, int rec_index, const RayIn& r, TT& T)
+template <bool PRUNED, class TT>
+__device__ __forceinline__ int leaf_record(const DevSceneView& sc, int rec_index, const RayIn& r, TT& T)
 {
     const float4* rec = sc.leaf_recs + 3 * (size_t)rec_index;
     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
-    leaf_record_regs(r0, r1, r2, r, T);
-}
-
-// Two consecutive records of one leaf: all six loads are issued before the first test so the second
-// record's latency hides behind the first record's arithmetic (the records are adjacent: 96 bytes).
-template <class TT>
-__device__ __forceinline__ void leaf_record_pair(const DevSceneView& sc, int rec_index, const RayIn& r, TT& T)
-{
-    const float4* rec = sc.leaf_recs + 3 * (size_t)rec_index;
-    const float4 a0 = __ldg(rec), a1 = __ldg(rec + 1), a2 = __ldg(rec + 2);
-    const float4 b0 = __ldg(rec + 3), b1 = __ldg(rec + 4), b2 = __ldg(rec + 5);
-    leaf_record_regs(a0, a1, a2, r, T);
-    leaf_record_regs(b0, b1, b2, r, T);
+    return leaf_record_regs<PRUNED>(r0, r1, r2, r, T);
 }
 
 // Scheduler 2 ("vote"): every busy lane is either at a node or inside a leaf.  Each round the warp
@@ -180,11 +174,11 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
                 if (active && in_leaf) {
                     // (loading both records up front was measured: 79 registers, 346 -> 281 Mrays/s)
                     const float best0 = T.best;
-                    leaf_record(sc, rec, r, T);
-                    if (++rec == rec_end) { in_leaf = false; need_pop = true; }
+                    rec += leaf_record<PRUNED>(sc, rec, r, T);
+                    if (rec >= rec_end) { in_leaf = false; need_pop = true; }
                     else {
-                        leaf_record(sc, rec, r, T);
-                        if (++rec == rec_end) { in_leaf = false; need_pop = true; }
+                        rec += leaf_record<PRUNED>(sc, rec, r, T);
+                        if (rec >= rec_end) { in_leaf = false; need_pop = true; }
                     }
                     // boolean queries (Scene::occluded) may stop once the answer can no longer change
                     if (T.best < best0 && src.decided(r, T.best)) {

@@ -116,12 +116,13 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 const float4 a = sm.a[slot], b = sm.b[slot];
                 RayIn r; r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
                 int4 e = sm.e[slot];
-                Trav T; T.best = sm.c[slot].w; T.res = e.x;
+                const float4 c = sm.c[slot];
+                Trav T; T.ix = c.x; T.iy = c.y; T.iz = c.z; T.best = c.w; T.res = e.x;
                 const float best0 = T.best;
 #pragma unroll
                 for (int s = 0; s < kPrimSteps; s++) {
-                    leaf_record(sc, e.y, r, T);
-                    if (++e.y == e.z) { leaf_done = true; break; }
+                    e.y += leaf_record<PRUNED>(sc, e.y, r, T);
+                    if (e.y >= e.z) { leaf_done = true; break; }
                 }
                 // boolean queries (Scene::occluded) stop once the answer can no longer change (occlusion_decided)
                 if (Src::kCanDecide && T.best < best0) {

@@ -144,19 +144,37 @@ WRT_HD bool trav_begin(const DevSceneView& sc, const RayIn& r, Trav& T)
 }
 
 // Entry AND exit distance of the ray through a conservative box (NaN slabs are ignored, i.e. never prune).
-WRT_HD void bound_interval(const float4 a, const float4 b, const RayIn& r, float ix, float iy, float iz, float& entry, float& exit_)
+WRT_HD void box_interval(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayIn& r,
+                         float ix, float iy, float iz, float& entry, float& exit_)
 {
-    float t0 = (a.z - r.ox) * ix, t1 = (b.y - r.ox) * ix;
+    float t0 = (lox - r.ox) * ix, t1 = (hix - r.ox) * ix;
     bool nn = (t0 != t0 || t1 != t1);
     const float ex = nn ? -HUGE_VALF : fminf(t0, t1), xx = nn ? HUGE_VALF : fmaxf(t0, t1);
-    t0 = (a.w - r.oy) * iy; t1 = (b.z - r.oy) * iy;
+    t0 = (loy - r.oy) * iy; t1 = (hiy - r.oy) * iy;
     nn = (t0 != t0 || t1 != t1);
     const float ey = nn ? -HUGE_VALF : fminf(t0, t1), xy = nn ? HUGE_VALF : fmaxf(t0, t1);
-    t0 = (b.x - r.oz) * iz; t1 = (b.w - r.oz) * iz;
+    t0 = (loz - r.oz) * iz; t1 = (hiz - r.oz) * iz;
     nn = (t0 != t0 || t1 != t1);
     const float ez = nn ? -HUGE_VALF : fminf(t0, t1), xz = nn ? HUGE_VALF : fmaxf(t0, t1);
     entry = fmaxf(ex, fmaxf(ey, ez));
     exit_ = fminf(xx, fminf(xy, xz));
+}
+
+WRT_HD void bound_interval(const float4 a, const float4 b, const RayIn& r, float ix, float iy, float iz, float& entry, float& exit_)
+{
+    box_interval(a.z, a.w, b.x, b.y, b.z, b.w, r, ix, iy, iz, entry, exit_);
+}
+
+// The PRUNED skip test on an explicit conservative box: nothing inside can change the traversal state when the
+// ray (a) enters the box later than best * (1 + 1e-4) or (b) does not enter it at all / only behind its origin.
+WRT_HD bool box_prunable(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayIn& r,
+                         float ix, float iy, float iz, int res, float best)
+{
+    float en, ex;
+    box_interval(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz, en, ex);
+    if (res >= 0 && en > best * WRT_PRUNE_REL) return true;
+    const float m = 1e-4f * (fabsf(en) + fabsf(ex)) + 1e-4f;
+    return (en > ex + m) || (ex < -m);
 }
 
 #ifndef WRT_MISS_PRUNE
@@ -171,11 +189,7 @@ WRT_HD bool trav_skip(const DevSceneView& sc, const float4 na, const RayIn& r, c
     // origin): a reported hit lies inside the bounds of its primitive, so nothing below can be hit.
     if (PRUNED) {
         const float4 nb = ldg4(&sc.nodes[2 * T.node + 1]);
-        float en, ex;
-        bound_interval(na, nb, r, T.ix, T.iy, T.iz, en, ex);
-        if (T.res >= 0 && en > T.best * WRT_PRUNE_REL) return true;
-        const float m = 1e-4f * (fabsf(en) + fabsf(ex)) + 1e-4f;
-        return (en > ex + m) || (ex < -m);
+        return box_prunable(na.z, na.w, nb.x, nb.y, nb.z, nb.w, r, T.ix, T.iy, T.iz, T.res, T.best);
     }
     return false;
 #else
@@ -244,7 +258,11 @@ WRT_HD void trav_interior_prune(const DevSceneView& sc, const float4 na, const R
     }
 }
 
-template <bool COUNT>
+// Leaf records (:359-374).  Besides one record per referenced primitive, in the reference's list order, a leaf holds
+// "skip" records (kind 2, scene_layout.cpp): the conservative box of the next `n` records.  PRUNED traversal jumps
+// over those records when the box is prunable — same argument as for sub-trees, and the order of the records that
+// ARE tested is unchanged; EXACT traversal ignores skip records.
+template <bool PRUNED, bool COUNT>
 WRT_HD void trav_leaf(const DevSceneView& sc, const float4 na, const RayIn& r, Trav& T, VisitCounters* vc)
 {
     const int first = f2i(na.x);
@@ -253,6 +271,13 @@ WRT_HD void trav_leaf(const DevSceneView& sc, const float4 na, const RayIn& r, T
         const float4* rec = sc.leaf_recs + 3 * (size_t)(first + i);
         const float4 r0 = ldg4(rec), r1 = ldg4(rec + 1), r2 = ldg4(rec + 2);
         float t; bool hit;
+        if (f2i(r2.w) == WRT_REC_SKIP) {
+            if (PRUNED) {
+                if (COUNT) vc->inner++;      // a bounds test, counted with the node visits
+                if (box_prunable(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r, T.ix, T.iy, T.iz, T.res, T.best)) i += f2i(r0.w);
+            }
+            continue;
+        }
         if (f2i(r2.w) == 0) {
             if (COUNT) vc->tri++;
             hit = triangle_t(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, t);
@@ -292,7 +317,7 @@ WRT_HD int kd_traverse(const DevSceneView& sc, const RayIn& r, float& best_t, Vi
                 continue;
             }
             if (COUNT) vc->leaf++;
-            trav_leaf<COUNT>(sc, na, r, T, vc);
+            trav_leaf<PRUNED, COUNT>(sc, na, r, T, vc);
         }
         if (!trav_pop(T, S)) break;
     }
