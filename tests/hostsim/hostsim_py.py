@@ -34,6 +34,9 @@ class HostSim:
         if rc:
             raise RuntimeError(err.value.decode())
 
+    def num_recs(self):
+        return int(lib().hs_num_recs(self.h))
+
     def trace_closest(self, rays8, pruned=True):
         r = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)
         prim = np.zeros(len(r), np.int32); t = np.zeros(len(r), np.float32)

@@ -61,6 +61,40 @@ def test_cuda_adversarial_vs_port(wrt, name):
         assert np.array_equal(a[4][hit], b[4][hit]) and np.array_equal(a[5][hit], b[5][hit])
 
 
+@pytest.mark.parametrize("knobs", [("2", "2"), ("5", "3"), ("16", "6")])
+def test_cuda_skip_record_layouts(wrt, monkeypatch, knobs):
+    """Leaf skip records at aggressive settings (every leaf chunked, nested groups): CUDA EXACT == CUDA PRUNED ==
+    oracle port on adversarial rays with infinite and finite ray.tmax, and on the occlusion query."""
+    monkeypatch.setenv("WRT_LEAF_SKIP_MIN", knobs[0]); monkeypatch.setenv("WRT_LEAF_SKIP_CHUNK", knobs[1])
+    sc = scenes.synthetic_torus_scene(n=96, width=64, height=64, n_spheres=2000)
+    port = engines.PortEngine(wrt, sc)
+    ex = engines.CudaEngine(wrt, sc, False); pr = engines.CudaEngine(wrt, sc, True)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 120000, seed=11))
+    short = rays.copy(); short[:, 7] = np.random.default_rng(11).uniform(0.05, 4.0, len(rays)).astype(np.float32)
+    for rr in (rays, short):
+        want = port.intersect(rr)
+        for e in (ex, pr):
+            got = e.intersect(rr)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(util.bits(got[1]), util.bits(want[1])), e.name
+    full = pr.intersect(rays, full=True)
+    q = scenes.nee_queries(full[2], (full[0] >= 0) & (full[5] > 0), sc.lights)
+    want = port.occluded(q)
+    assert np.array_equal(pr.occluded(q), want) and np.array_equal(ex.occluded(q), want)
+
+
+def test_cuda_nan_interval_terminates_like_the_reference(wrt):
+    """See tests/test_hostsim.py::test_nan_interval_terminates_like_the_reference — same rays through the kernels,
+    embedded in a batch large enough to run through the pooled scheduler."""
+    sc = scenes.synthetic_torus_scene(n=96, width=64, height=64, n_spheres=2000)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 60000))
+    port = engines.PortEngine(wrt, sc)
+    want = port.intersect(rays)
+    assert want[0][13289] == 965
+    for pruned in (False, True):
+        got = engines.CudaEngine(wrt, sc, pruned).intersect(rays)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(util.bits(got[1]), util.bits(want[1]))
+
+
 @pytest.mark.parametrize("name", ["torus", "cbox_dragon", "bunny", "synthetic_1m"])
 def test_exact_equals_pruned_large(wrt, name):
     """T1b: >= 1e7 rays per scene (primary at 4 sub-pixel offsets, secondary from the hits, random)."""

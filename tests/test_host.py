@@ -41,6 +41,22 @@ def test_kd_build_matches_reference_live(wrt, have_ref, make):
     assert np.array_equal(a["first_ref"][~inner], b["first_ref"][~inner])
 
 
+def test_parallel_kd_build_equals_serial(wrt, monkeypatch):
+    """The multi-threaded build (concurrent axis sorts, per-axis event distribution, sub-tree tasks spliced back in
+    DFS pre-order) must emit the same arrays, index for index, as the serial build (WRT_KD_THREADS=1) — large enough
+    to take every parallel path (> 200 000 events per axis, > 4096 primitives per task)."""
+    sc = scenes.synthetic_torus_scene(n=240, width=64, height=64, n_spheres=2000)
+    monkeypatch.setenv("WRT_KD_THREADS", "1")
+    a = util.host_scene(wrt, sc).arrays()["tree"]
+    for threads in ("2", "7", "64"):
+        monkeypatch.setenv("WRT_KD_THREADS", threads)
+        b = util.host_scene(wrt, sc).arrays()["tree"]
+        for k in ("axis", "left", "right", "first_ref", "nref", "refs"):
+            assert np.array_equal(a[k], b[k]), (threads, k)
+        assert np.array_equal(util.bits(a["split"]), util.bits(b["split"]))
+        assert np.array_equal(util.bits(a["root_box"]), util.bits(b["root_box"]))
+
+
 def test_scene_loader_matches_reference(wrt, have_ref):
     """Our XML/OBJ loader vs Scene::loadScene on torus.scene (needs /root/reference: build container only)."""
     from oracle import refpy

@@ -34,6 +34,44 @@ def test_hostsim_exact_equals_pruned_and_port(wrt, name):
         assert np.array_equal(a[4][hit], x[4][hit]) and np.array_equal(a[5][hit], x[5][hit])
 
 
+@pytest.mark.parametrize("knobs", [("2", "2"), ("5", "3"), ("16", "6")])
+def test_hostsim_skip_record_layouts(wrt, monkeypatch, knobs):
+    """Leaf skip records (scene_layout.cpp) at aggressive settings — every leaf of >= 2 entries chunked, nested
+    groups everywhere — must not change a single result: EXACT (ignores them) == PRUNED (jumps over prunable
+    chunks) == oracle port, on adversarial rays with infinite AND finite ray.tmax (the reference ends the whole
+    traversal at the first popped node with ray.tmax < tmin, KDtreeAccel.cpp:323)."""
+    monkeypatch.setenv("WRT_LEAF_SKIP_MIN", knobs[0]); monkeypatch.setenv("WRT_LEAF_SKIP_CHUNK", knobs[1])
+    sc = scenes.synthetic_torus_scene(n=64, width=64, height=64, n_spheres=500)
+    ex = engines.HostSimEngine(wrt, sc, False); pr = engines.HostSimEngine(wrt, sc, True)
+    monkeypatch.setenv("WRT_LEAF_SKIP", "0")
+    plain = engines.HostSimEngine(wrt, sc, True)
+    assert pr.sim.num_recs() > plain.sim.num_recs()          # the layout really contains skip records
+    port = engines.PortEngine(wrt, sc)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 30000, seed=7))
+    short = rays.copy(); short[:, 7] = np.random.default_rng(7).uniform(0.05, 4.0, len(rays)).astype(np.float32)
+    for rr in (rays, short):
+        want = port.intersect(rr)
+        for e in (ex, pr, plain):
+            got = e.intersect(rr)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(util.bits(got[1]), util.bits(want[1])), e.name
+    q = scenes.nee_queries(*(lambda a: (a[2], (a[0] >= 0) & (a[5] > 0)))(pr.intersect(rays, full=True)), sc.lights)
+    assert np.array_equal(pr.occluded(q), port.occluded(q)) and np.array_equal(ex.occluded(q), port.occluded(q))
+
+
+def test_nan_interval_terminates_like_the_reference(wrt):
+    """Regression (found by the adversarial batch while testing a child-pair scheduler): an axis-parallel ray whose
+    origin lies exactly on split planes produces NaN kd intervals; the reference then pops an entry with
+    tmin = +inf, sees ray.tmax < tmin and BREAKS, leaving a closer primitive in a later entry untested."""
+    sc = scenes.synthetic_torus_scene(n=96, width=64, height=64, n_spheres=2000)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 60000))[13280:13300]
+    port = engines.PortEngine(wrt, sc)
+    want = port.intersect(rays)
+    assert want[0][9] == 965                                   # the reference's (non-closest) answer for ray 13289
+    for pruned in (False, True):
+        got = engines.HostSimEngine(wrt, sc, pruned).intersect(rays)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(util.bits(got[1]), util.bits(want[1]))
+
+
 def test_visit_counters_match_port(wrt):
     """Reference-semantics work counters (the B_ray inputs of the roofline) agree with the instrumented port."""
     sc, z = scenes.load_fixture("cbox_dragon")

@@ -211,9 +211,9 @@ void fill_camera(const wrt_camera* c, DevCamera& d)
 static int pool_capacity()
 {
     const char* e = getenv("WRT_POOL_PATHS");
-    long v = e ? atol(e) : (1L << 24);
+    long v = e ? atol(e) : (1L << 26);
     if (v < 1024) v = 1024;
-    if (v > (1L << 26)) v = 1L << 26;
+    if (v > (1L << 27)) v = 1L << 27;
     return (int)v;
 }
 

@@ -66,30 +66,35 @@ int env_int(const char* name, int dflt, int lo, int hi)
     const int v = atoi(e);
     return v < lo ? lo : (v > hi ? hi : v);
 }
-// smaller leaves are tested record by record (tuning knobs: WRT_LEAF_SKIP_MIN, WRT_LEAF_SKIP_CHUNK)
-int skip_min_leaf() { static const int v = env_int("WRT_LEAF_SKIP_MIN", 16, 2, 1 << 20); return v; }
-int skip_chunk() { static const int v = env_int("WRT_LEAF_SKIP_CHUNK", 6, 2, 64); return v; }
+// Tuning knobs, read once per build_layout call: WRT_LEAF_SKIP=0 disables skip records, WRT_LEAF_SKIP_MIN = smallest
+// leaf that gets them (smaller leaves are tested record by record), WRT_LEAF_SKIP_CHUNK = target chunk length.
+// Defaults measured on C3 / C5 (profiles/r1_experiments.md, "Skip records").
+struct SkipCfg { bool enabled; int min_leaf, chunk; };
 
-bool skip_records_enabled()
+SkipCfg skip_config()
 {
     const char* e = getenv("WRT_LEAF_SKIP");
-    return !(e && e[0] == '0');
+    SkipCfg c;
+    c.enabled = !(e && e[0] == '0');
+    c.min_leaf = env_int("WRT_LEAF_SKIP_MIN", 16, 2, 1 << 20);
+    c.chunk = env_int("WRT_LEAF_SKIP_CHUNK", 6, 2, 64);
+    return c;
 }
 
-void plan_leaf(int c, bool enabled, std::vector<int>& chunks, int& per_group)
+void plan_leaf(int c, const SkipCfg& cfg, std::vector<int>& chunks, int& per_group)
 {
     chunks.clear(); per_group = 0;
-    if (!enabled || c < skip_min_leaf()) return;
-    const int g = skip_chunk();
+    if (!cfg.enabled || c < cfg.min_leaf) return;
+    const int g = cfg.chunk;
     const int k = std::max(1, (c + g / 2) / g);
     for (int j = 0; j < k; j++) chunks.push_back(c / k + (j < c % k ? 1 : 0));
     if (k >= kSkipGroupMinChunks) per_group = 4;
 }
 
-int64_t leaf_record_count(int c, bool enabled)
+int64_t leaf_record_count(int c, const SkipCfg& cfg)
 {
     std::vector<int> chunks; int per_group;
-    plan_leaf(c, enabled, chunks, per_group);
+    plan_leaf(c, cfg, chunks, per_group);
     int64_t n = c + (int64_t)chunks.size();
     if (per_group) for (size_t j = 0; j < chunks.size(); j += per_group) if (chunks.size() - j >= 2) n++;
     return n;
@@ -163,7 +168,7 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
     const int n_live = (int)order.size();
 
     // ---- leaf records --------------------------------------------------------------------------
-    const bool skips = skip_records_enabled();
+    const SkipCfg skips = skip_config();
     std::vector<int64_t> first_rec(n_live, 0);
     std::vector<int32_t> leaf_recs_n(n_live, 0);
     int64_t n_recs = 0;

@@ -55,7 +55,7 @@ struct ClosestSrc {
 };
 
 template <bool PRUNED>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, WRT_MIN_BLOCKS)
 k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int32_t* __restrict__ prim,
                 float* __restrict__ t_out, float* __restrict__ p3, float* __restrict__ n3,
                 int32_t* __restrict__ inside, int32_t* __restrict__ matid, unsigned long long* counter, float4* scratch)
@@ -74,7 +74,7 @@ struct AnySrc {
 };
 
 template <bool PRUNED>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, WRT_MIN_BLOCKS)
 k_trace_any(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, uint8_t* __restrict__ hit,
             unsigned long long* counter, float4* scratch)
 {
@@ -96,7 +96,7 @@ struct ShadowTestSrc {
 };
 
 template <bool PRUNED>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, WRT_MIN_BLOCKS)
 k_trace_shadow(DevSceneView sc, const wrt_ray* __restrict__ rays, const float* __restrict__ target3, size_t n,
                float* __restrict__ visible, unsigned long long* counter, float4* scratch)
 {
@@ -133,7 +133,7 @@ struct OccludedSrc {
 };
 
 template <bool PRUNED>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, WRT_MIN_BLOCKS)
 k_trace_occluded(DevSceneView sc, const float* __restrict__ q9, size_t n, uint8_t* __restrict__ occluded,
                  unsigned long long* counter, float4* scratch)
 {

@@ -34,6 +34,12 @@ constexpr int kNodeSteps = WRT_POOL_NODE_STEPS;
 constexpr int kPrimSteps = WRT_POOL_PRIM_STEPS;
 constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 
+// __launch_bounds__ second argument of the traversal kernels: 8 blocks of 128 threads caps them at 56 registers, which
+// keeps 9 blocks (36 warps) resident per SM; without the cap ptxas takes 67 registers = 7 blocks (C3: 1271 -> 1352 Mrays/s).
+#ifndef WRT_MIN_BLOCKS
+#define WRT_MIN_BLOCKS 8
+#endif
+
 struct PoolSmem {
     float4 a[kPoolRays];               // ox oy oz dx
     float4 b[kPoolRays];               // dy dz ray.tmin ray.tmax

@@ -9,9 +9,7 @@
 namespace wrt {
 
 constexpr int kBlock = 128;
-#ifndef WRT_MIN_BLOCKS
-#define WRT_MIN_BLOCKS 1               /* __launch_bounds__ second argument of the traversal kernels (register cap) */
-#endif
+
 
 __device__ __forceinline__ RayIn pool_load_ray(const PathPool& pool, uint32_t slot)
 {

@@ -9,7 +9,10 @@
 // re-sorting the per-child event lists (:192-276).  The design differences are in the plumbing only:
 // nodes are emitted straight into flat arrays (DFS pre-order), objects are indices not pointers, and
 // a node's event lists are released as soon as its children own theirs (the reference keeps them all:
-// ~2 GB at 1 M triangles).
+// ~2 GB at 1 M triangles).  The build is also parallel where that cannot change the result: the three initial
+// event sorts run concurrently, the per-axis event distribution of large nodes runs on three threads, and the
+// sub-trees below the top few levels are built as independent tasks into private arrays that are spliced back in
+// DFS pre-order — the output arrays are identical, index for index, to the serial build's (tests/test_host.py).
 //
 // All float expressions keep the reference's operand order; this file must be compiled without FMA
 // contraction (-ffp-contract=off, no -march=native).
@@ -17,6 +20,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <future>
+#include <thread>
 #include "host_scene.h"
 
 namespace wrt {
@@ -98,46 +103,41 @@ int find_split(const BuildNode& nd, Real* split_out)
     return best_axis;
 }
 
+int emit_leaf(FlatTree& out, const BuildNode& nd, int dep)
+{
+    int me = (int)out.axis.size();
+    out.axis.push_back(-1); out.split.push_back(0.f);
+    out.left.push_back(-1); out.right.push_back(-1);
+    out.first_ref.push_back((int32_t)out.refs.size());
+    out.n_ref.push_back((int32_t)nd.objs.size());
+    out.refs.insert(out.refs.end(), nd.objs.begin(), nd.objs.end());
+    if (dep > out.depth) out.depth = dep;
+    return me;
+}
+
+constexpr size_t kParallelAxisMin = 200000;   // events per axis above which the three axes are distributed concurrently
+
 struct Builder {
     const std::vector<float>& boxes;  // 6 per prim
-    FlatTree& out;
     int dep_max;
 
-    int emit_leaf(const BuildNode& nd, int dep)
+    // One node of buildTree(), KDtreeAccel.cpp:118-276: termination test, split search, classification and the
+    // children's object / event lists.  Returns false when *nd stays a leaf; otherwise consumes nd's lists and
+    // returns the children (nd itself is left empty, the caller deletes it).
+    bool split_node(BuildNode* nd, int dep, int& axis, Real& split, BuildNode*& l, BuildNode*& r) const
     {
-        int me = (int)out.axis.size();
-        out.axis.push_back(-1); out.split.push_back(0.f);
-        out.left.push_back(-1); out.right.push_back(-1);
-        out.first_ref.push_back((int32_t)out.refs.size());
-        out.n_ref.push_back((int32_t)nd.objs.size());
-        out.refs.insert(out.refs.end(), nd.objs.begin(), nd.objs.end());
-        if (dep > out.depth) out.depth = dep;
-        return me;
-    }
-
-    // buildTree(), KDtreeAccel.cpp:118-307.  Consumes (and frees) *nd.
-    int build(BuildNode* nd, int dep)
-    {
-        if (dep > dep_max || nd->objs.size() <= 1) {
-            int me = emit_leaf(*nd, dep);
-            delete nd;
-            return me;
-        }
-        Real split = 0.f;
-        int axis = find_split(*nd, &split);
-        if (axis < 0) {
-            // No plane with cost < INF-EPS.  The reference indexes box.l[-1] here (undefined
-            // behaviour); the only defined reading of the node it leaves is a leaf (axis == -1).
-            int me = emit_leaf(*nd, dep);
-            delete nd;
-            return me;
-        }
+        if (dep > dep_max || nd->objs.size() <= 1) return false;
+        split = 0.f;
+        axis = find_split(*nd, &split);
+        // No plane with cost < INF-EPS.  The reference indexes box.l[-1] here (undefined behaviour); the only
+        // defined reading of the node it leaves is a leaf (axis == -1).
+        if (axis < 0) return false;
         const int n = (int)nd->objs.size();
         enum { LeftOnly = 0, RightOnly = 1, Both = 2 };
         std::vector<unsigned char> div(n);
         std::vector<int32_t> to_l(n), to_r(n);
-        BuildNode* l = new BuildNode();
-        BuildNode* r = new BuildNode();
+        l = new BuildNode();
+        r = new BuildNode();
         int nl = 0, nr = 0, nb = 0;
         for (int i = 0; i < n; i++) {  // :142-163
             const float* b = &boxes[6 * (size_t)nd->objs[i]];
@@ -155,7 +155,9 @@ struct Builder {
                 to_r[i] = (int)r->objs.size(); r->objs.push_back(nd->objs[i]);
             }
         }
-        for (int a = 0; a < 3; a++) {  // :203-276; children inherit the parent's order, never re-sorted
+        const int split_axis = axis;
+        const Real split_pos = split;
+        auto distribute = [&](int a) {  // :203-276; children inherit the parent's order, never re-sorted
             std::vector<Event>& pe = nd->ev[a];
             l->ev[a].reserve(l->objs.size() * 2);
             r->ev[a].reserve(r->objs.size() * 2);
@@ -166,19 +168,26 @@ struct Builder {
                 const int d = div[s.index];
                 if (d == LeftOnly) { e.pos = s.pos; e.index = to_l[s.index]; l->ev[a].push_back(e); }
                 else if (d == RightOnly) { e.pos = s.pos; e.index = to_r[s.index]; r->ev[a].push_back(e); }
-                else if (a != axis) {
+                else if (a != split_axis) {
                     e.pos = s.pos;
                     e.index = to_l[s.index]; l->ev[a].push_back(e);
                     e.index = to_r[s.index]; r->ev[a].push_back(e);
                 } else if (s.type == kEnd) {     // straddler's end: clipped to the plane on the left
-                    e.pos = split; e.index = to_l[s.index]; l->ev[a].push_back(e);
+                    e.pos = split_pos; e.index = to_l[s.index]; l->ev[a].push_back(e);
                     e.pos = s.pos; e.index = to_r[s.index]; r->ev[a].push_back(e);
                 } else if (s.type == kStart) {   // straddler's start: clipped on the right
                     e.pos = s.pos; e.index = to_l[s.index]; l->ev[a].push_back(e);
-                    e.pos = split; e.index = to_r[s.index]; r->ev[a].push_back(e);
+                    e.pos = split_pos; e.index = to_r[s.index]; r->ev[a].push_back(e);
                 }
             }
             std::vector<Event>().swap(pe);  // parent's list is no longer needed
+        };
+        if (nd->ev[0].size() >= kParallelAxisMin) {   // the axes are independent: same lists, three threads
+            std::thread t1(distribute, 1), t2(distribute, 2);
+            distribute(0);
+            t1.join(); t2.join();
+        } else {
+            for (int a = 0; a < 3; a++) distribute(a);
         }
         BuildNode* kids[2] = { l, r };
         for (int k = 0; k < 2; k++) {  // :277-294 — child box = first/last event per axis
@@ -189,19 +198,73 @@ struct Builder {
                 for (int a = 0; a < 3; a++) { c->lo[a] = 0.f; c->hi[a] = 0.f; }
         }
         std::vector<int32_t>().swap(nd->objs);
-        delete nd;
-        std::vector<unsigned char>().swap(div);
-        std::vector<int32_t>().swap(to_l);
-        std::vector<int32_t>().swap(to_r);
+        return true;
+    }
 
+    // buildTree(), KDtreeAccel.cpp:118-307, serial: nodes are appended to `out` in DFS pre-order.  Consumes *nd.
+    int build(BuildNode* nd, int dep, FlatTree& out) const
+    {
+        int axis; Real split; BuildNode* l; BuildNode* r;
+        const int n = (int)nd->objs.size();
+        if (!split_node(nd, dep, axis, split, l, r)) {
+            int me = emit_leaf(out, *nd, dep);
+            delete nd;
+            return me;
+        }
+        delete nd;
         int me = (int)out.axis.size();
         out.axis.push_back(axis); out.split.push_back(split);
         out.left.push_back(-1); out.right.push_back(-1);
         out.first_ref.push_back(-1); out.n_ref.push_back(n);
-        int li = build(l, dep + 1);
-        int ri = build(r, dep + 1);
+        int li = build(l, dep + 1, out);
+        int ri = build(r, dep + 1, out);
         out.left[me] = li; out.right[me] = ri;
         return me;
+    }
+
+    // Appends sub-tree `t` (its own indices start at 0) to `out`; returns the index its root gets.
+    static int splice(FlatTree& out, const FlatTree& t)
+    {
+        const int32_t node_off = (int32_t)out.axis.size();
+        const int32_t ref_off = (int32_t)out.refs.size();
+        out.axis.insert(out.axis.end(), t.axis.begin(), t.axis.end());
+        out.split.insert(out.split.end(), t.split.begin(), t.split.end());
+        out.n_ref.insert(out.n_ref.end(), t.n_ref.begin(), t.n_ref.end());
+        for (size_t i = 0; i < t.axis.size(); i++) {
+            out.left.push_back(t.left[i] < 0 ? -1 : t.left[i] + node_off);
+            out.right.push_back(t.right[i] < 0 ? -1 : t.right[i] + node_off);
+            out.first_ref.push_back(t.first_ref[i] < 0 ? -1 : t.first_ref[i] + ref_off);
+        }
+        out.refs.insert(out.refs.end(), t.refs.begin(), t.refs.end());
+        if (t.depth > out.depth) out.depth = t.depth;
+        return node_off;
+    }
+
+    // Same tree, the two sub-trees of the top `levels` levels built concurrently into private arrays and spliced
+    // back in pre-order (node, left sub-tree, right sub-tree): identical output to build().
+    void build_parallel(BuildNode* nd, int dep, FlatTree& out, int levels) const
+    {
+        if (levels <= 0 || nd->objs.size() < 4096) { build(nd, dep, out); return; }
+        int axis; Real split; BuildNode* l; BuildNode* r;
+        const int n = (int)nd->objs.size();
+        if (!split_node(nd, dep, axis, split, l, r)) {
+            emit_leaf(out, *nd, dep);
+            delete nd;
+            return;
+        }
+        delete nd;
+        FlatTree lt, rt;
+        lt.depth = rt.depth = 0;
+        std::future<void> fl = std::async(std::launch::async, [&] { build_parallel(l, dep + 1, lt, levels - 1); });
+        build_parallel(r, dep + 1, rt, levels - 1);
+        fl.get();
+        const int me = (int)out.axis.size();
+        out.axis.push_back(axis); out.split.push_back(split);
+        out.left.push_back(-1); out.right.push_back(-1);
+        out.first_ref.push_back(-1); out.n_ref.push_back(n);
+        const int li = splice(out, lt);
+                const int ri = splice(out, rt);
+        out.left[me] = li; out.right[me] = ri;
     }
 };
 
@@ -233,6 +296,11 @@ bool build_kdtree(HostScene& hs, std::string& err)
     std::vector<float> boxes((size_t)n * 6);
     for (int i = 0; i < n; i++) prim_box(hs.prim_kind[i], &hs.prim_data[9 * (size_t)i], &boxes[6 * (size_t)i]);
 
+    // WRT_KD_THREADS=1 forces the serial build (the tests compare the two)
+    int threads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("WRT_KD_THREADS")) threads = atoi(e);
+    if (threads < 1) threads = 1;
+
     // KDtreeAccel::init, KDtreeAccel.cpp:12-57
     hs.tree.dep_max = (int)(1.2 * std::log((double)n) + 2.0);
     BuildNode* root = new BuildNode();
@@ -245,16 +313,28 @@ bool build_kdtree(HostScene& hs, std::string& err)
             e[2 * (size_t)j].type = kStart; e[2 * (size_t)j].pos = boxes[6 * (size_t)j + a]; e[2 * (size_t)j].index = j;
             e[2 * (size_t)j + 1].type = kEnd; e[2 * (size_t)j + 1].pos = boxes[6 * (size_t)j + 3 + a]; e[2 * (size_t)j + 1].index = j;
         }
-        // libc qsort on purpose: the comparator is not a strict weak order, so the result depends on
-        // the sorting algorithm; the reference's tree is whatever libc qsort makes of it.
-        qsort(e.data(), e.size(), sizeof(Event), compare_events);
-        root->lo[a] = e.front().pos;
-        root->hi[a] = e.back().pos;
+    }
+    {   // libc qsort on purpose: the comparator is not a strict weak order, so the result depends on
+        // the sorting algorithm; the reference's tree is whatever libc qsort makes of it.  The three arrays are
+        // independent, so they are sorted concurrently.
+        auto sort_axis = [&](int a) { qsort(root->ev[a].data(), root->ev[a].size(), sizeof(Event), compare_events); };
+        if (threads > 1) { std::thread t1(sort_axis, 1), t2(sort_axis, 2); sort_axis(0); t1.join(); t2.join(); }
+        else for (int a = 0; a < 3; a++) sort_axis(a);
+    }
+    for (int a = 0; a < 3; a++) {
+        root->lo[a] = root->ev[a].front().pos;
+        root->hi[a] = root->ev[a].back().pos;
     }
     for (int a = 0; a < 3; a++) { hs.tree.root_box[a] = root->lo[a]; hs.tree.root_box[3 + a] = root->hi[a]; }
 
-    Builder b = { boxes, hs.tree, hs.tree.dep_max };
-    b.build(root, 1);
+    Builder b = { boxes, hs.tree.dep_max };
+    if (threads > 1) {
+        int levels = 1;
+        while ((1 << levels) < 2 * threads && levels < 7) levels++;   // ~2 tasks per thread
+        b.build_parallel(root, 1, hs.tree, levels);
+    } else {
+        b.build(root, 1, hs.tree);
+    }
     hs.tree_built = true;
 
     // sceneSphere, scene.cpp:481-487
