@@ -201,6 +201,12 @@ int wrt_render_pt(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, 
 /* Device film (accumulated into: caller zeroes it); no host copy; asynchronous on `stream`. */
 int wrt_render_pt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film_hw3,
                       void* stream);
+/* WhittedIntegrator: SurfaceIntegrator::render + WhittedIntegrator::raytracing (surfaceIntegrator.cpp:14-46,
+ * whitted.cpp:17-113).  Same parameters as path tracing: max_depth = MAX_TRACING_DEPTH,
+ * one light sample per hit.  Pixels the reference leaves NaN (a light seen from its back side, unoccluded) are NaN. */
+int wrt_render_whitted(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* film_hw3);
+int wrt_render_whitted_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film_hw3,
+                           void* stream);
 /* BidirPathTracing::render (bidirPathTracing.cpp:23-265) with the shipped controlLength gating. */
 int wrt_render_bdpt(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* film_hw3);
 int wrt_render_bdpt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p,

@@ -14,6 +14,7 @@
 #include "scene/scene.h"
 #include "surfaceIntegrator/pathIntegrator.h"
 #include "surfaceIntegrator/bidirPathTracing.h"
+#include "surfaceIntegrator/whitted.h"
 #include "material/bsdf.h"
 #include <unordered_map>
 #include <vector>
@@ -34,11 +35,12 @@ extern "C" Geometry* __wrap__ZN11KDtreeAccel8traverseERK3RayP15KDtreeAccelNode(
 namespace {
 
 struct RefHandle {
-    int kind;  // 0 = path tracer, 1 = bidirectional path tracer
+    int kind;  // 0 = path tracer, 1 = bidirectional path tracer, 2 = Whitted
     PathIntegrator* pt;
     BidirPathTracing* bpt;
+    WhittedIntegrator* wh;
     std::unordered_map<const Geometry*, int> index_of;
-    SurfaceIntegrator* integ() { return kind == 0 ? (SurfaceIntegrator*)pt : (SurfaceIntegrator*)bpt; }
+    SurfaceIntegrator* integ() { return kind == 0 ? (SurfaceIntegrator*)pt : kind == 1 ? (SurfaceIntegrator*)bpt : (SurfaceIntegrator*)wh; }
     Scene& scene() { return integ()->scene; }
 };
 
@@ -113,8 +115,11 @@ extern "C" {
 void* ref_create(int kind)
 {
     RefHandle* h = new RefHandle();
-    h->kind = kind; h->pt = 0; h->bpt = 0;
-    if (kind == 0) {
+    h->kind = kind; h->pt = 0; h->bpt = 0; h->wh = 0;
+    if (kind == 2) {
+        h->wh = new WhittedIntegrator();
+        h->wh->maxTracingDepth = 7; h->wh->samplesPerPixel = 1;
+    } else if (kind == 0) {
         h->pt = new PathIntegrator();
         h->pt->maxTracingDepth = 7; h->pt->samplesPerPixel = 1;
         h->pt->samplesOfLight = 8; h->pt->samplesOfHemisphere = 4;
@@ -406,6 +411,21 @@ int ref_render_pt(void* hv, int spp, int max_depth, unsigned seed, float* film)
     clear_film(h->pt->film);
     h->pt->render();
     copy_film(h->pt->film, film);
+    return 0;
+}
+
+// WhittedIntegrator: SurfaceIntegrator::render() with WhittedIntegrator::raytracing (R/src/surfaceIntegrator/whitted.cpp).
+// The light pick uses libc rand() (:28), seeded here as well.
+int ref_render_whitted(void* hv, int spp, int max_depth, unsigned seed, float* film)
+{
+    RefHandle* h = (RefHandle*)hv;
+    if (h->kind != 2) return -1;
+    h->wh->samplesPerPixel = spp; h->wh->maxTracingDepth = max_depth;
+    h->wh->rng.seed(seed); h->wh->rng.mti = RNG::N;
+    srand(seed);
+    clear_film(h->wh->film);
+    h->wh->render();
+    copy_film(h->wh->film, film);
     return 0;
 }
 

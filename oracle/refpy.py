@@ -60,12 +60,12 @@ def fixed_torus_scene(dst_dir=None):
 
 
 class RefScene:
-    """One reference integrator (+ its Scene).  kind: 'pt' or 'bdpt'."""
+    """One reference integrator (+ its Scene).  kind: 'pt', 'bdpt' or 'whitted'."""
 
     def __init__(self, kind="pt"):
         self.L = lib()
         self.kind = kind
-        self.h = C.c_void_p(self.L.ref_create(0 if kind == "pt" else 1))
+        self.h = C.c_void_p(self.L.ref_create({"pt": 0, "bdpt": 1, "whitted": 2}[kind]))
         self.width = self.height = 0
 
     # -- construction -------------------------------------------------------------------------
@@ -173,6 +173,11 @@ class RefScene:
         f = np.zeros((self.height, self.width, 3), np.float32) if want_film else None
         assert self.L.ref_render_pt_rows(self.h, spp, max_depth, C.c_uint(seed), row0, row1, row_stride, col0,
                                          col1, _fp(f) if want_film else None) == 0
+        return f
+
+    def render_whitted(self, spp, max_depth, seed=5489):
+        f = np.zeros((self.height, self.width, 3), np.float32)
+        assert self.L.ref_render_whitted(self.h, spp, max_depth, C.c_uint(seed), _fp(f)) == 0
         return f
 
     def render_bdpt(self, iterations, seed=5489, control_length=3, max_path_length=10):

@@ -10,6 +10,7 @@
 #include "scene_layout.h"
 #include "pt_logic.cuh"
 #include "bdpt_logic.cuh"
+#include "whitted_logic.cuh"
 
 using namespace wrt;
 
@@ -116,6 +117,51 @@ void hs_visits_per_ray(void* hv, const wrt_ray* rays, size_t n, int pruned, unsi
         if (pruned) kd_traverse<true, true>(sc, r, tt, &vc); else kd_traverse<false, true>(sc, r, tt, &vc);
         leaf[i] = vc.leaf; tri[i] = vc.tri + vc.sph;
     }
+}
+
+// Sequential driver of whitted_shade (the per-node code of k_wh_shade) with an explicit list of parked children.
+void hs_render_whitted(void* hv, const wrt_camera* cam, const wrt_pt_params* p, int pruned, float* film,
+                       unsigned long long* rays_out)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    PtParams P;
+    P.width = p->width; P.height = p->height; P.spp = p->spp; P.max_depth = p->max_depth; P.seed = p->seed;
+    P.strata = (int)std::sqrt((double)p->spp); if (P.strata < 1) P.strata = 1;
+    P.sample_first = p->sample_first; P.sample_stride = p->sample_stride > 0 ? p->sample_stride : 1;
+    P.local_spp = (P.spp - P.sample_first + P.sample_stride - 1) / P.sample_stride;
+    P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->spp;
+    P.total_samples = (unsigned long long)P.width * P.height * (unsigned long long)P.local_spp;
+    DevCamera dc; cam_fill(cam, dc);
+    unsigned long long nrays = 0;
+    struct Item { RayIn r; float w; int dep; };
+    std::vector<Item> todo;
+    for (unsigned long long s = 0; s < P.total_samples; s++) {
+        RayIn r; PathData pd;
+        pt_generate(P, dc, s, r, pd);
+        float* px = film + 3 * (size_t)pd.pixel;
+        todo.clear();
+        todo.push_back(Item{ r, 1.f, 0 });
+        while (!todo.empty()) {
+            const Item it = todo.back(); todo.pop_back();
+            float t;
+            const int prim = hs_traverse(sc, it.r, pruned, t);
+            nrays++;
+            WhittedOut out;
+            whitted_shade(sc, P.max_depth, it.r, it.dep, it.w, pd.rng, prim, t, out);
+            if (out.emit) { px[0] += out.emit_c.x * P.film_scale; px[1] += out.emit_c.y * P.film_scale; px[2] += out.emit_c.z * P.film_scale; }
+            if (out.shadow) {
+                RayIn sr;
+                make_ray(out.q[0], out.q[1], out.q[2], out.q[3], out.q[4], out.q[5], sr);
+                nrays++;
+                if (hs_visible(sc, sr, pruned, out.q[6], out.q[7], out.q[8])) {
+                    px[0] += out.shadow_c.x * P.film_scale; px[1] += out.shadow_c.y * P.film_scale; px[2] += out.shadow_c.z * P.film_scale;
+                }
+            }
+            if (out.trans.valid) todo.push_back(Item{ out.trans.ray, out.trans.w, it.dep + 1 });
+            if (out.reflect.valid) todo.push_back(Item{ out.reflect.ray, out.reflect.w, it.dep + 1 });
+        }
+    }
+    if (rays_out) *rays_out = nrays;
 }
 
 // Sequential driver of the same pt_generate / pt_shade the CUDA kernels call.

@@ -72,6 +72,13 @@ class HostSim:
                            C.byref(rays))
         return film, rays.value
 
+    def render_whitted(self, cam, params, pruned=True):
+        film = np.zeros((params.height, params.width, 3), np.float32)
+        rays = C.c_ulonglong(0)
+        lib().hs_render_whitted(self.h, C.byref(cam), C.byref(params), int(pruned), film.ctypes.data_as(C.c_void_p),
+                                C.byref(rays))
+        return film, rays.value
+
     def render_bdpt(self, cam, params, pruned=True):
         film = np.zeros((params.height, params.width, 3), np.float32)
         rays = C.c_ulonglong(0)

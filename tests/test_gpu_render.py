@@ -101,6 +101,65 @@ def test_hostsim_equals_cuda_pt(wrt):
     assert abs(float(s.closest_rays + s.shadow_rays) - rays) <= 0.002 * rays
 
 
+# ---- Whitted ------------------------------------------------------------------------
+def _whitted_compare(mine, r1, r2):
+    """The reference's Whitted image contains NaN pixels by construction (light seen from its back side, unoccluded:
+    0 * 0 / 0 at whitted.cpp:37-38).  Compare the NaN masks, then the finite pixels statistically."""
+    n1, n2, nm = np.isnan(r1).any(2), np.isnan(r2).any(2), np.isnan(mine).any(2)
+    ok = ~(n1 | n2 | nm)
+    rm = (r1 + r2) * 0.5
+    return dict(mask_mismatch=int((n1 != nm).sum()), mask_floor=int((n1 != n2).sum()), nan_ref=int(n1.sum()),
+                mean=float(mine[ok].mean()), mean_ref=float(rm[ok].mean()),
+                err=float(np.abs(mine[ok] - rm[ok]).mean()), floor=float(np.abs(r1[ok] - r2[ok]).mean()))
+
+
+@pytest.mark.parametrize("name", ["cornell", "small_mixed"])
+def test_whitted_image_parity_with_reference(wrt, have_ref, name):
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.cornell_box_scene(96, 96) if name == "cornell" else scenes.small_mixed_scene(96, 96)
+    hs = util.host_scene(wrt, sc); scene = wrt.Scene(hs)
+    gpu = scene.render_whitted(hs.camera(), wrt.PtParams(96, 96, 16, 7, 1, 0, 1, 0.0))
+    ref = util.ref_scene(sc, "whitted")
+    c = _whitted_compare(gpu, ref.render_whitted(16, 7, seed=5489), ref.render_whitted(16, 7, seed=31))
+    print(name, c)
+    assert c["nan_ref"] > 0
+    assert c["mask_mismatch"] <= 1.5 * c["mask_floor"] + 8           # NaN pixels where the reference has them
+    assert abs(c["mean"] - c["mean_ref"]) <= 0.01 * c["mean_ref"]    # 1 % of mean radiance
+    assert c["err"] <= 1.1 * c["floor"]                              # closer to the 2-seed mean than the seeds are to each other
+
+
+def test_whitted_properties_and_hostsim(wrt):
+    """Sharding sums to the single call, pool-size independence, EXACT == PRUNED, and the sequential CPU build of the
+    same per-node code (hostsim, explicit list of parked children) gives the same image as the wavefront (pending lists)."""
+    import os
+    from hostsim_py import HostSim
+    sc = scenes.small_mixed_scene(64, 48)
+    hs = util.host_scene(wrt, sc); scene = wrt.Scene(hs); cam = hs.camera()
+    p = wrt.PtParams(64, 48, 16, 7, 5, 0, 1, 0.0)
+    a = scene.render_whitted(cam, p)
+    nan = np.isnan(a)
+    def same(x, y):
+        return np.array_equal(np.isnan(x), np.isnan(y)) and np.allclose(np.nan_to_num(x), np.nan_to_num(y), rtol=1e-4, atol=1e-6)
+    assert same(scene.render_whitted(cam, p), a)
+    parts = sum(scene.render_whitted(cam, wrt.PtParams(64, 48, 16, 7, 5, g, 4, 0.0)) for g in range(4))
+    assert same(parts, a)
+    os.environ["WRT_POOL_PATHS"] = "2048"
+    scene2 = wrt.Scene(hs)
+    c = scene2.render_whitted(cam, p)
+    del os.environ["WRT_POOL_PATHS"]
+    assert same(c, a)
+    scene.set_traversal(wrt.TRAVERSE_EXACT)
+    assert same(scene.render_whitted(cam, p), a)
+    scene.set_traversal(wrt.TRAVERSE_PRUNED)
+    scene.reset_stats(); scene.render_whitted(cam, p); s = scene.stats()
+    cpu, rays = HostSim(hs.desc(), hs).render_whitted(cam, p)
+    assert (np.isnan(cpu) != nan).sum() <= 0.002 * nan.size
+    ok = ~(np.isnan(cpu) | nan)
+    assert np.abs(cpu[ok] - a[ok]).mean() <= 0.01 * a[ok].mean()
+    assert abs(float(s.closest_rays + s.shadow_rays) - rays) <= 0.002 * rays
+
+
 # ---- BDPT ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["cornell", "small_mixed"])
 def test_bdpt_image_parity_with_reference(wrt, have_ref, name):

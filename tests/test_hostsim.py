@@ -101,6 +101,29 @@ def test_empty_and_ragged_inputs(wrt):
     assert prim[0] == -1 and prim[2] >= 0
 
 
+def test_hostsim_whitted_matches_reference(wrt, have_ref):
+    """the per-node Whitted code (whitted_logic.cuh, compiled for the CPU) against the reference's
+    WhittedIntegrator.  The reference image has NaN pixels by construction (0 * 0 / 0 for a light seen from its
+    back side, whitted.cpp:37-38): the NaN masks must agree as well as two reference seeds agree with each other,
+    and the finite pixels statistically."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from hostsim_py import HostSim
+    res, spp = 48, 16
+    for sc in (scenes.small_mixed_scene(res, res), scenes.cornell_box_scene(res, res)):
+        hs = util.host_scene(wrt, sc); sim = HostSim(hs.desc(), hs)
+        mine, rays = sim.render_whitted(hs.camera(), wrt.PtParams(res, res, spp, 7, 11, 0, 1, 0.0))
+        ref = util.ref_scene(sc, "whitted"); ref.reset_traverse_calls()
+        r1 = ref.render_whitted(spp, 7, seed=5489); calls = ref.traverse_calls(); r2 = ref.render_whitted(spp, 7, seed=31)
+        n1, n2, nm = np.isnan(r1).any(2), np.isnan(r2).any(2), np.isnan(mine).any(2)
+        assert n1.sum() > 0 and (n1 != nm).sum() <= 1.5 * (n1 != n2).sum() + 8
+        ok = ~(n1 | n2 | nm)
+        rm = (r1 + r2) * 0.5
+        assert abs(mine[ok].mean() - rm[ok].mean()) <= 0.01 * rm[ok].mean()
+        assert np.abs(mine[ok] - rm[ok]).mean() <= 1.1 * np.abs(r1[ok] - r2[ok]).mean()
+        assert 0.7 * calls <= rays <= 1.001 * calls      # black connections are not traced; never more rays than the reference
+
+
 def _block_mean(img, b):
     h, w, c = img.shape
     return img[: h // b * b, : w // b * b].reshape(h // b, b, w // b, b, c).mean(axis=(1, 3))

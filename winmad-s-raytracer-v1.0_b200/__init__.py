@@ -94,7 +94,7 @@ EXPORTS = [
     "wrt_get_stats",
     "wrt_reset_stats", "wrt_trace_closest", "wrt_trace_closest_full", "wrt_trace_any", "wrt_trace_shadow",
     "wrt_trace_occluded", "wrt_trace_closest_dev", "wrt_trace_occluded_dev", "wrt_trace_count_visits",
-    "wrt_render_pt", "wrt_render_pt_dev", "wrt_render_bdpt", "wrt_render_bdpt_dev", "wrt_film_resolve_dev",
+    "wrt_render_pt", "wrt_render_pt_dev", "wrt_render_whitted", "wrt_render_whitted_dev", "wrt_render_bdpt", "wrt_render_bdpt_dev", "wrt_film_resolve_dev",
 ]
 
 _lib = None
@@ -415,6 +415,16 @@ class Scene:
         _check(lib().wrt_render_pt_dev(self._sc, C.byref(cam), C.byref(params), C.c_void_p(d_film),
                                        C.c_void_p(stream or 0)), "wrt_render_pt_dev")
 
+    def render_whitted(self, cam, params, film=None):
+        """WhittedIntegrator (whitted.cpp:17-113); params: PtParams (max_depth = MAX_TRACING_DEPTH)."""
+        film = np.zeros((params.height, params.width, 3), np.float32) if film is None else film
+        _check(lib().wrt_render_whitted(self._sc, C.byref(cam), C.byref(params), _ptr(film, _f32p)), "wrt_render_whitted")
+        return film
+
+    def render_whitted_dev(self, cam, params, d_film, stream=None):
+        _check(lib().wrt_render_whitted_dev(self._sc, C.byref(cam), C.byref(params), C.c_void_p(d_film),
+                                            C.c_void_p(stream or 0)), "wrt_render_whitted_dev")
+
     def render_bdpt(self, cam, params, film=None):
         film = np.zeros((params.height, params.width, 3), np.float32) if film is None else film
         _check(lib().wrt_render_bdpt(self._sc, C.byref(cam), C.byref(params), _ptr(film, _f32p)), "wrt_render_bdpt")
@@ -474,6 +484,24 @@ class PathIntegrator(SurfaceIntegrator):
 
     def render(self):
         self.film = self.scene.render_pt(self.host_scene.camera(), self.params())
+        return self.film
+
+
+class WhittedIntegrator(SurfaceIntegrator):
+    """WhittedIntegrator::init / render / outputImage (whitted.cpp:3-15, surfaceIntegrator.cpp:14-51)."""
+
+    def init(self, scene_file, para):
+        self.maxTracingDepth = para.MAX_TRACING_DEPTH
+        self.samplesPerPixel = para.SAMPLES_PER_PIXEL
+        self._init_scene(scene_file, para)
+        return self
+
+    def params(self, sample_first=0, sample_stride=1, film_scale=0.0):
+        return PtParams(self.width, self.height, self.samplesPerPixel, self.maxTracingDepth, self.seed,
+                        sample_first, sample_stride, film_scale)
+
+    def render(self):
+        self.film = self.scene.render_whitted(self.host_scene.camera(), self.params())
         return self.film
 
 

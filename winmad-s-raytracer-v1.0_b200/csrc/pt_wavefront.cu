@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <string>
 #include "pt_logic.cuh"
+#include "whitted_logic.cuh"
 #include "wavefront_kernels.cuh"
 
 namespace wrt {
@@ -88,6 +89,99 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
         const unsigned long long gpos = warp_append(&counters[WF_WORK4], regen);
         if (alive) { pool_store(pool, slot, r, pd); queue_out[qpos] = slot; }                 // continuing paths: front
         if (regen) { pool_store(pool, slot, r, pd); queue_out[cap - 1 - gpos] = slot; }       // new camera rays: back
+    }
+}
+
+// ---- Whitted (whitted_logic.cuh): same pool and queues; meta.w = dep | pending << 16; weight.x = w -------------------
+struct WhittedPending {        // the parked second child of every level of a slot's ray tree: [level][slot]
+    float4* o;                 // origin, w
+    float4* d;                 // direction, dep (int bits)
+};
+
+__device__ __forceinline__ void wh_store(const PathPool& pool, uint32_t slot, const RayIn& r, float w, uint32_t pixel, const Rng& rng,
+                                         int dep, int pending)
+{
+    float4* p = reinterpret_cast<float4*>(pool.ray + slot);
+    p[0] = make_float4(r.ox, r.oy, r.oz, r.dx);
+    p[1] = make_float4(r.dy, r.dz, r.tmin, r.tmax);
+    pool.weight_pdf[slot] = make_float4(w, 0.f, 0.f, 0.f);
+    pool.meta[slot] = make_uint4(pixel, rng.key, rng.ctr, (uint32_t)dep | ((uint32_t)pending << 16));
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_wh_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0, unsigned long long first_sample)
+{
+    for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n0; s += gridDim.x * blockDim.x) {
+        RayIn r; PathData pd;
+        pt_generate(P, cam, first_sample + s, r, pd);
+        wh_store(pool, s, r, 1.f, pd.pixel, pd.rng, 0, 0);
+        queue[s] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_wh_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in, size_t n,
+           uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* counters,
+           unsigned long long* next_sample, size_t n_gen_in, size_t cap, WhittedPending pend, int levels)
+{
+    size_t base;
+    while (next_chunk(&counters[WF_WORK2], n, base)) {
+        const size_t e = base + (threadIdx.x & 31);
+        const bool valid = e < n;
+        uint32_t slot = 0, pixel = 0;
+        RayIn r; Rng rng = { 0u, 0u }; WhittedOut out;
+        float w = 0.f; int dep = 0, pending = 0;
+        out.emit = false; out.shadow = false; out.reflect.valid = false; out.trans.valid = false;
+        if (valid) {
+            slot = queue_slot(queue_in, e, n_gen_in, cap);
+            r = pool_load_ray(pool, slot);
+            const uint4 m = pool.meta[slot];
+            w = pool.weight_pdf[slot].x;
+            pixel = m.x; rng.key = m.y; rng.ctr = m.z; dep = (int)(m.w & 0xffffu); pending = (int)(m.w >> 16);
+            whitted_shade(sc, P.max_depth, r, dep, w, rng, pool.hit_prim[slot], pool.hit_t[slot], out);
+            if (out.emit) film_add(film, pixel, out.emit_c, P.film_scale);
+        }
+        const unsigned long long spos = warp_append(&counters[WF_SHADOW_COUNT], valid && out.shadow);
+        if (valid && out.shadow) {
+            sq.a[spos] = make_float4(out.q[0], out.q[1], out.q[2], out.shadow_c.x);
+            sq.b[spos] = make_float4(out.q[3], out.q[4], out.q[5], out.shadow_c.y);
+            sq.c[spos] = make_float4(out.q[6], out.q[7], out.q[8], out.shadow_c.z);
+            sq.pixel[spos] = pixel;
+        }
+        // next ray of this slot: a child of this node, else the most recently parked child, else a new camera sample
+        bool alive = false;
+        if (valid) {
+            if (out.reflect.valid) {
+                if (out.trans.valid && pending < levels) {
+                    const size_t at = (size_t)pending * cap + slot;
+                    const RayIn& q = out.trans.ray;
+                    pend.o[at] = make_float4(q.ox, q.oy, q.oz, out.trans.w);
+                    pend.d[at] = make_float4(q.dx, q.dy, q.dz, __int_as_float(dep + 1));
+                    pending++;
+                }
+                r = out.reflect.ray; w = out.reflect.w; dep += 1; alive = true;
+            } else if (out.trans.valid) {
+                r = out.trans.ray; w = out.trans.w; dep += 1; alive = true;
+            } else if (pending > 0) {
+                pending--;
+                const size_t at = (size_t)pending * cap + slot;
+                const float4 o = pend.o[at], d = pend.d[at];
+                r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmin = 0.f; r.tmax = WRT_INF;
+                w = o.w; dep = __float_as_int(d.w); alive = true;
+            }
+        }
+        const bool dead = valid && !alive;
+        const unsigned long long snew = warp_append(next_sample, dead);
+        const bool regen = dead && snew < P.total_samples;
+        if (regen) {
+            PathData pd;
+            pt_generate(P, cam, snew, r, pd);
+            w = 1.f; pixel = pd.pixel; rng = pd.rng; dep = 0; pending = 0;
+        }
+        const unsigned long long qpos = warp_append(&counters[WF_NEXT_COUNT], alive);
+        const unsigned long long gpos = warp_append(&counters[WF_WORK4], regen);
+        if (alive) { wh_store(pool, slot, r, w, pixel, rng, dep, pending); queue_out[qpos] = slot; }
+        if (regen) { wh_store(pool, slot, r, w, pixel, rng, dep, pending); queue_out[cap - 1 - gpos] = slot; }
     }
 }
 
@@ -185,7 +279,7 @@ static void wavefront_free(wrt_wavefront* wf)
     cudaFree(wf->pool.hit_prim); cudaFree(wf->pool.hit_t);
     cudaFree(wf->queue[0]); cudaFree(wf->queue[1]);
     cudaFree(wf->shadow.a); cudaFree(wf->shadow.b); cudaFree(wf->shadow.c); cudaFree(wf->shadow.pixel);
-    cudaFree(wf->counters); cudaFreeHost(wf->h_counters); cudaFree(wf->film); cudaFree(wf->trav_scratch);
+    cudaFree(wf->counters); cudaFreeHost(wf->h_counters); cudaFree(wf->film); cudaFree(wf->trav_scratch); cudaFree(wf->whitted);
     for (int i = 0; i < wf->n_ev; i++) cudaEventDestroy(wf->ev[i]);
     delete[] wf->ev;
     if (wf->stream) cudaStreamDestroy(wf->stream);
@@ -245,9 +339,10 @@ static int sub_pools()
 // long rays, ~3.5 ms on the 1 M-triangle scene) is covered by the bulk of another's.
 struct PtPlan { int k; int cap[8]; };
 
-static void pt_plan(const PtParams& P, PtPlan& plan)
+static void pt_plan(const PtParams& P, PtPlan& plan, bool whitted = false)
 {
     unsigned long long total = std::min<unsigned long long>((unsigned long long)pool_capacity(), P.total_samples);
+    if (whitted) total = std::min<unsigned long long>(total, 1ull << 23);    // + 32 bytes x (maxTracingDepth + 1) of pending list per slot
     total = std::max<unsigned long long>(total, 1024ull);
     int k = sub_pools();
     if (total < (1ull << 18)) k = 1;
@@ -257,10 +352,26 @@ static void pt_plan(const PtParams& P, PtPlan& plan)
 }
 
 struct SubState {
-    wrt_wavefront* wf; size_t n; size_t n_gen; int cur; bool in_flight; int timed;
+    wrt_wavefront* wf; size_t n; size_t n_gen; int cur; bool in_flight; int timed; int index;
 };
 
-static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st)
+// Per-sub-pool pending lists of the Whitted integrator: (max_depth + 1) levels x capacity x 32 bytes.
+static int whitted_pending(wrt_wavefront* wf, int levels, WhittedPending& out)
+{
+    const size_t need = (size_t)levels * (size_t)wf->capacity * 2 * sizeof(float4);
+    if (wf->whitted_bytes < need) {
+        if (wf->whitted) cudaFree(wf->whitted);
+        wf->whitted = nullptr; wf->whitted_bytes = 0;
+        WRT_CUDA(cudaMalloc(&wf->whitted, need));
+        wf->whitted_bytes = need;
+    }
+    out.o = (float4*)wf->whitted;
+    out.d = out.o + (size_t)levels * (size_t)wf->capacity;
+    return WRT_OK;
+}
+
+static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st,
+                            bool whitted = false)
 {
     if (!cam) { set_error("wrt_render_pt: null camera"); return WRT_ERR_INVALID; }
     if (sc->view.n_lights <= 0) { set_error("wrt_render_pt: the scene has no light (the reference indexes an empty vector here)"); return WRT_ERR_INVALID; }
@@ -268,13 +379,16 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     int rc = pt_fill_params(p, P);
     if (rc) return rc;
     DevCamera dc; fill_camera(cam, dc);
-    PtPlan plan; pt_plan(P, plan);
+    PtPlan plan; pt_plan(P, plan, whitted);
     SubState sub[8];
+    const int wh_levels = std::min(P.max_depth + 1, 64);
+    WhittedPending wh_pend[8];
     for (int j = 0; j < plan.k; j++) {
         rc = wavefront_get_slot(sc, j, plan.cap[j], &sub[j].wf);
         if (rc) return rc;
         rc = wavefront_events(sub[j].wf, 4 * 64);
         if (rc) return rc;
+        if (whitted) { rc = whitted_pending(sub[j].wf, wh_levels, wh_pend[j]); if (rc) return rc; }
     }
     const bool pruned = sc->traversal_mode == WRT_TRAVERSE_PRUNED;
     const bool counting = sc->counting != 0;
@@ -284,6 +398,7 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     static int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
     static int g_ext_e = persistent_grid_for((const void*)k_pt_extend<false>, kBlock);
     static int g_shade = persistent_grid_for((const void*)k_pt_shade, kBlock);
+    static int g_wshade = persistent_grid_for((const void*)k_wh_shade, kBlock);
     static int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
     static int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
     static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count<false>, kBlock);
@@ -296,9 +411,10 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         const unsigned long long left = P.total_samples - first;
         const unsigned n0 = (unsigned)std::min<unsigned long long>((unsigned long long)plan.cap[j], left);
         WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
-        if (n0) k_pt_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first);
+        if (n0 && whitted) k_wh_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first);
+        else if (n0) k_pt_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first);
         WRT_CUDA(cudaGetLastError());
-        sub[j].n = n0; sub[j].n_gen = 0; sub[j].cur = 0; sub[j].in_flight = false; sub[j].timed = 0;
+        sub[j].n = n0; sub[j].n_gen = 0; sub[j].cur = 0; sub[j].in_flight = false; sub[j].timed = 0; sub[j].index = j;
         first += n0;
         sc->stats.kernel_launches += n0 ? 1 : 0;
     }
@@ -326,8 +442,10 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch, ng, cap);
         else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch, ng, cap);
         if (ev) cudaEventRecord(ev[1], q);
-        k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
-                                              d_film, wf->counters, next_sample, ng, cap);
+        if (whitted) k_wh_shade<<<g_wshade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
+                                                            d_film, wf->counters, next_sample, ng, cap, wh_pend[s.index], wh_levels);
+        else k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
+                                                   d_film, wf->counters, next_sample, ng, cap);
         if (ev) cudaEventRecord(ev[2], q);
         if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
         else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
@@ -409,6 +527,20 @@ int wrt_render_pt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params*
     return WRT_OK;
 }
 
+int wrt_render_whitted_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, void* stream)
+{
+    if (!sc || !d_film) { set_error("wrt_render_whitted_dev: null argument"); return WRT_ERR_INVALID; }
+    WRT_CUDA(cudaSetDevice(sc->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
+    WRT_CUDA(cudaEventRecord(sc->ev0, st));
+    int rc = render_pt_device(sc, cam, p, d_film, st, true);
+    if (rc) return rc;
+    WRT_CUDA(cudaEventRecord(sc->ev1, st));
+    WRT_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f; WRT_CUDA(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1)); sc->stats.last_render_ms = ms;
+    return WRT_OK;
+}
+
 int wrt_film_resolve_dev(const float* d_film, int32_t width, int32_t height, float scale, float gamma, uint8_t* d_rgb, void* stream)
 {
     if (!d_film || !d_rgb || width <= 0 || height <= 0 || !(gamma > 0.f)) { set_error("wrt_film_resolve_dev: bad argument"); return WRT_ERR_INVALID; }
@@ -420,7 +552,19 @@ int wrt_film_resolve_dev(const float* d_film, int32_t width, int32_t height, flo
     return WRT_OK;
 }
 
+static int render_pt_host(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* film, bool whitted);
+
 int wrt_render_pt(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* film)
+{
+    return render_pt_host(sc, cam, p, film, false);
+}
+
+int wrt_render_whitted(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* film)
+{
+    return render_pt_host(sc, cam, p, film, true);
+}
+
+static int render_pt_host(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* film, bool whitted)
 {
     if (!sc || !film || !p) { set_error("wrt_render_pt: null argument"); return WRT_ERR_INVALID; }
     WRT_CUDA(cudaSetDevice(sc->device));
@@ -429,7 +573,7 @@ int wrt_render_pt(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, 
     if (rc) return rc;
     wrt_wavefront* wf = nullptr;
     {   // grow sub-pool 0 first: re-creating it frees the film it owns
-        PtPlan plan; pt_plan(P, plan);
+        PtPlan plan; pt_plan(P, plan, whitted);
         rc = wavefront_get_slot(sc, 0, plan.cap[0], &wf);
         if (rc) return rc;
     }
@@ -440,7 +584,7 @@ int wrt_render_pt(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, 
     cudaStream_t st = sc->stream;
     WRT_CUDA(cudaEventRecord(sc->ev0, st));
     WRT_CUDA(cudaMemsetAsync(d_film, 0, floats * sizeof(float), st));
-    rc = render_pt_device(sc, cam, p, d_film, st);
+    rc = render_pt_device(sc, cam, p, d_film, st, whitted);
     if (rc) return rc;
     WRT_CUDA(cudaEventRecord(sc->ev1, st));
     WRT_CUDA(cudaMemcpyAsync(film, d_film, floats * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -51,6 +51,7 @@ struct wrt_wavefront {
     float* film; size_t film_floats;    // library-owned device film for host-buffer entry points
     void* bdpt;                         // BDPT-only buffers (bdpt_wavefront.cu)
     size_t bdpt_bytes;
+    void* whitted; size_t whitted_bytes; // Whitted-only pending lists (pt_wavefront.cu)
     cudaEvent_t* ev; int n_ev;          // stage-timing events (4 per iteration)
     void* trav_scratch; size_t trav_scratch_bytes;   // pooled scheduler's traversal stacks for this sub-pool's launches
     cudaStream_t stream;                // this sub-pool's own stream (PT runs sub-pools concurrently)

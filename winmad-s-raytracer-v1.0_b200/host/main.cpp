@@ -66,6 +66,9 @@ int main(int argc, char* argv[])
     if (!strcmp(argv[3], "-p")) {
         wrt_pt_params p = { para.WIDTH, para.HEIGHT, para.SAMPLES_PER_PIXEL, para.MAX_TRACING_DEPTH, 0u, 0, 1, 0.f };
         rc = wrt_render_pt(sc, &cam, &p, film.data());
+    } else if (!strcmp(argv[3], "-r")) {          // main.cpp:34-38 WhittedIntegrator
+        wrt_pt_params p = { para.WIDTH, para.HEIGHT, para.SAMPLES_PER_PIXEL, para.MAX_TRACING_DEPTH, 0u, 0, 1, 0.f };
+        rc = wrt_render_whitted(sc, &cam, &p, film.data());
     } else if (!strcmp(argv[3], "-bpt")) {
         // BidirPathTracing::init: min/max path length 0/10, 1 iteration, controlLength 3; outputImage transposes
         wrt_bdpt_params p = { para.WIDTH, para.HEIGHT, 1, 0, 10, 3, 0u, 0, 1, 0.f, 1 };
