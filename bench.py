@@ -41,6 +41,8 @@ WORKLOADS = {
                integrator="pt", width=3840, height=2160, spp=16, depth=5, n=2237, n_spheres=100000),
     "c5_small": dict(desc="C5 at 1/5 scale: 2,000,000-triangle displaced torus + 20,000 spheres, 3840x2160 PT, depth 5, 16 spp",
                      integrator="pt", width=3840, height=2160, spp=16, depth=5, n=1000, n_spheres=20000),
+    "whitted_torus": dict(desc="Whitted (SURVEY 8(f)4): torus.scene (13,486 triangles, glass + diffuse), 512x512, depth 7, 256 spp",
+                          integrator="whitted", width=512, height=512, spp=256, depth=7, fixture="torus"),
     "c4": dict(desc="C4: closed Cornell box + area light, BDPT 1440x1440, 16 iterations per step (of 256), controlLength 3",
                integrator="bdpt", width=1440, height=1440, iterations=16, n=0),
 }
@@ -111,7 +113,7 @@ def _ref_worker(conn, w, rank, nproc):
     try:
         from oracle import refpy
         sc = make_scene(w)
-        kind = "pt" if w["integrator"] == "pt" else "bdpt"
+        kind = w["integrator"]
         ref = refpy.RefScene(kind)
         t0 = time.time()
         ref.build(sc.materials, sc.kind, sc.data, sc.matid, sc.lights, sc.cam12, sc.width, sc.height)
@@ -131,6 +133,9 @@ def _ref_worker(conn, w, rank, nproc):
                     ref.render_pt_rows(1, w["depth"], 5489 + rank + 97 * msg, rank * stride, sc.height, 0, cw,
                                        want_film=False, row_stride=nproc * stride)
                 samples = n_rows * cw
+            elif kind == "whitted":
+                ref.render_whitted(1, w["depth"], seed=5489 + rank + 97 * msg)     # whole frame per process
+                samples = sc.width * sc.height
             else:
                 ref.render_bdpt(1, seed=5489 + rank + 97 * msg)
                 samples = sc.width * sc.height
@@ -189,6 +194,8 @@ def reference_workload(w):
     if w["integrator"] == "pt":
         # bounded sample: 1 spp on every k-th row of the whole frame (same ray mix as the full frame)
         w["row_stride"] = 8 if w["width"] * w["height"] >= 2 ** 20 else 2
+    elif w["integrator"] == "whitted":
+        w["row_stride"] = 1              # whole frame at 1 spp per process
     else:
         w["width"] = w["height"] = 256   # BDPT must render whole (square) frames: 1 iteration at 256^2
         w["row_stride"] = 1
@@ -209,12 +216,14 @@ def main():
 
     w = dict(WORKLOADS[args.workload])
     if args.spp:
-        w["spp" if w["integrator"] == "pt" else "iterations"] = args.spp
+        w["iterations" if w["integrator"] == "bdpt" else "spp"] = args.spp
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     metric, unit = "path-tracing ray throughput (closest-hit + shadow rays)", "Mrays/s"
     if w["integrator"] == "bdpt":
         metric = "bidirectional path-tracing ray throughput (closest-hit + connection rays)"
+    if w["integrator"] == "whitted":
+        metric = "Whitted ray-tree throughput (closest-hit + occlusion rays)"
 
     # ---------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -229,8 +238,12 @@ def main():
         res, build_s = run_reference(rw, args.steps, max(args.warmup, 1), nproc)
         rays = sum(r[0] for r in res); samples = sum(r[1] for r in res); secs = sum(r[2] for r in res)
         v = rays / secs / 1e6
-        sample = ("1 spp on every %d-th row of the %dx%d frame per step, rows dealt round-robin to %d independent reference processes"
-                  % (rw["row_stride"], rw["width"], rw["height"], nproc))
+        if rw["integrator"] == "pt":
+            sample = ("1 spp on every %d-th row of the %dx%d frame per step, rows dealt round-robin to %d independent reference processes"
+                      % (rw["row_stride"], rw["width"], rw["height"], nproc))
+        else:
+            sample = ("1 %s of the whole %dx%d frame per step in each of %d independent reference processes"
+                      % ("iteration" if rw["integrator"] == "bdpt" else "spp", rw["width"], rw["height"], nproc))
         line = {"metric": metric, "value": v, "unit": unit, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(len(res), 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -265,18 +278,20 @@ def main():
     cam = hs.camera()
     npix = w["width"] * w["height"]
 
-    if w["integrator"] == "pt":
+    if w["integrator"] in ("pt", "whitted"):
         spp = w["spp"]
+        whitted = w["integrator"] == "whitted"
 
         def params(scale):
             return W.PtParams(w["width"], w["height"], spp, w["depth"], 1000 + rank, 0, 1, scale)
 
         def render_dev(film):
             film.zero_()
-            scene.render_pt_dev(cam, params(1.0 / (spp * world)), film.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            fn = scene.render_whitted_dev if whitted else scene.render_pt_dev
+            fn(cam, params(1.0 / (spp * world)), film.data_ptr(), torch.cuda.current_stream().cuda_stream)
 
         def render_host(buf):
-            scene.render_pt(cam, params(0.0), buf)
+            (scene.render_whitted if whitted else scene.render_pt)(cam, params(0.0), buf)
         samples_per_step = npix * spp
     else:
         iters = w["iterations"]
@@ -344,7 +359,7 @@ def main():
     st = scene.stats()
     rays = float(st.closest_rays + st.shadow_rays)
     launches = int(st.kernel_launches)
-    mean_radiance = float(film.mean().item()) if rank == 0 else 0.0
+    mean_radiance = float(torch.nanmean(film).item()) if rank == 0 else 0.0   # Whitted films hold the reference's NaN pixels
     if dist is not None:
         tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
         rr = torch.tensor([rays, float(launches)], dtype=torch.float64, device="cuda"); dist.all_reduce(rr)
@@ -383,7 +398,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "integrator": w["integrator"], "traversal": "pruned (bit-exact vs exact, tests/test_gpu_traversal.py)",
                    "per_gpu": "full frame, %d %s per GPU, disjoint RNG streams; films summed by one NCCL reduce" %
-                              (w.get("spp", w.get("iterations")), "spp" if w["integrator"] == "pt" else "iterations"),
+                              (w.get("spp", w.get("iterations")), "iterations" if w["integrator"] == "bdpt" else "spp"),
                    "l2": "inputs larger than L2: the path pool (2^24 slots x 176 B in 2 concurrent sub-pools) is rewritten every bounce; the scene is meant to stay L2-resident",
                    "prims": int(sc.n_prims), "kd_build_s": round(kd_build_s, 2), "upload_s": round(upload_s, 2)},
         "samples_per_s": total_samples / (ms / 1e3), "rays_per_sample": rays / total_samples,
@@ -432,7 +447,7 @@ def main():
 
 def C_sizeof_inputs(W, w):
     import ctypes
-    return ctypes.sizeof(W.Camera) + ctypes.sizeof(W.PtParams if w["integrator"] == "pt" else W.BdptParams)
+    return ctypes.sizeof(W.Camera) + ctypes.sizeof(W.BdptParams if w["integrator"] == "bdpt" else W.PtParams)
 
 
 def cpu_baseline(w, unit):
