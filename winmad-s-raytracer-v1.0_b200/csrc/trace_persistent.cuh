@@ -93,12 +93,12 @@ __device__ __forceinline__ bool occlusion_decided(const RayIn& r, float best, fl
 
 // One leaf record against the ray + the reference's acceptance rule (KDtreeAccel.cpp:363-373).
 // Returns how many records to advance: 1, or 1 + n for a prunable skip record (PRUNED only).
-// (TT: any traversal state with `best`, `res` and invDir `ix, iy, iz`.)
+// (TT: any traversal state with `best`, `res`, invDir `ix, iy, iz` and `degen`.)
 template <bool PRUNED, class TT>
 __device__ __forceinline__ int leaf_record_regs(const float4 r0, const float4 r1, const float4 r2, const RayIn& r, TT& T)
 {
     if (__float_as_int(r2.w) == WRT_REC_SKIP) {
-        if (PRUNED && box_prunable(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r, T.ix, T.iy, T.iz, T.res, T.best)) return 1 + __float_as_int(r0.w);
+        if (PRUNED && box_prunable(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r, T.ix, T.iy, T.iz, T.res, T.best, T.degen)) return 1 + __float_as_int(r0.w);
         return 1;
     }
     if (__float_as_int(r2.w) == 0) {

@@ -34,17 +34,17 @@ constexpr int kNodeSteps = WRT_POOL_NODE_STEPS;
 constexpr int kPrimSteps = WRT_POOL_PRIM_STEPS;
 constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 
-// __launch_bounds__ second argument of the traversal kernels: 8 blocks of 128 threads caps them at 56 registers, which
-// keeps 9 blocks (36 warps) resident per SM; without the cap ptxas takes 67 registers = 7 blocks (C3: 1271 -> 1352 Mrays/s).
+// __launch_bounds__ second argument of the traversal kernels: 9 blocks of 128 threads caps them at 56 registers, which
+// keeps 9 blocks (36 warps, the shared-memory limit) resident per SM; without the cap ptxas takes 67 registers = 7 blocks (C3: 1271 -> 1352 Mrays/s).
 #ifndef WRT_MIN_BLOCKS
-#define WRT_MIN_BLOCKS 8
+#define WRT_MIN_BLOCKS 9
 #endif
 
 struct PoolSmem {
     float4 a[kPoolRays];               // ox oy oz dx
     float4 b[kPoolRays];               // dy dz ray.tmin ray.tmax
     float4 c[kPoolRays];               // ix iy iz best
-    float4 d[kPoolRays];               // T.tmin T.tmax node(int) sp|need_pop<<30 (int)
+    float4 d[kPoolRays];               // T.tmin T.tmax node(int) sp | degenerate << 29 | need_pop << 30 (int)
     int4 e[kPoolRays];                 // res rec rec_end item
     unsigned char ring[3][kPoolRays];  // 0 node, 1 prim, 2 free
 };
@@ -88,7 +88,7 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                             sm.a[slot] = make_float4(r.ox, r.oy, r.oz, r.dx);
                             sm.b[slot] = make_float4(r.dy, r.dz, r.tmin, r.tmax);
                             sm.c[slot] = make_float4(T.ix, T.iy, T.iz, T.best);
-                            sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(0), __int_as_float(0));
+                            sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(0), __int_as_float(T.degen ? (1 << 29) : 0));
                             sm.e[slot] = make_int4(-1, 0, 0, (int)item);
                             started = true;
                         } else src.done(item, r, -1, WRT_INF);
@@ -124,6 +124,7 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 int4 e = sm.e[slot];
                 const float4 c = sm.c[slot];
                 Trav T; T.ix = c.x; T.iy = c.y; T.iz = c.z; T.best = c.w; T.res = e.x;
+                T.degen = (__float_as_int(sm.d[slot].w) >> 29) & 1;
                 const float best0 = T.best;
 #pragma unroll
                 for (int s = 0; s < kPrimSteps; s++) {
@@ -171,6 +172,7 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 T.node = __float_as_int(d.z);
                 const int spw = __float_as_int(d.w);
                 T.sp = spw & 0xffff;
+                T.degen = (spw >> 29) & 1;
                 bool need_pop = (spw >> 30) & 1;
                 int4 e = sm.e[slot];
                 T.res = e.x;
@@ -180,20 +182,24 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                         need_pop = false;
                         if (T.sp <= 0) { next = 2; break; }
                         --T.sp;
-                        const float4 q = stk[(size_t)T.sp * kPoolRays];
+                        const float4 q = stk[(unsigned)T.sp * (unsigned)kPoolRays];
                         T.node = __float_as_int(q.x); T.tmin = q.y; T.tmax = q.z;
                     }
                     if (r.tmax < T.tmin) { next = 2; break; }                              // KDtreeAccel.cpp:323
-                    const float4 na = __ldg(&sc.nodes[2 * T.node]);
-                    if (trav_skip<PRUNED>(sc, na, r, T)) { need_pop = true; continue; }
-                    const unsigned packed = __float_as_uint(na.y);
-                    if ((packed & 3u) == WRT_LEAF_TAG) {
-                        const int cntl = (int)(packed >> 2);
-                        if (cntl > 0) { e.y = __float_as_int(na.x); e.z = e.y + cntl; next = 1; break; }
-                        need_pop = true;
-                        continue;
+                    const float4* np = sc.nodes + 2 * (size_t)T.node;
+                    const float4 na = __ldg(np);
+                    bool skip = false;
+                    if (PRUNED) {
+                        const float4 nb = __ldg(np + 1);
+                        skip = box_prunable(na.z, na.w, nb.x, nb.y, nb.z, nb.w, r, T.ix, T.iy, T.iz, T.res, T.best, T.degen);
                     }
-                    // interior step: trav_interior with the push going to the global scratch stack
+                    const unsigned packed = __float_as_uint(na.y);
+                    const unsigned hi = packed >> 2;                  // child pair (interior) | record count (leaf)
+                    const bool leaf = (packed & 3u) == WRT_LEAF_TAG;
+                    if (skip || (leaf && hi == 0u)) { need_pop = true; continue; }
+                    if (leaf) { e.y = __float_as_int(na.x); e.z = e.y + (int)hi; next = 1; break; }
+                    // interior step (trav_interior, KDtreeAccel.cpp:325-358) without branches; the push goes to the
+                    // global scratch stack
                     const int axis = (int)(packed & 3u);
                     const float split = na.x;
                     const float o_a = sel3(axis, r.ox, r.oy, r.oz);
@@ -201,21 +207,19 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                     const float i_a = sel3(axis, T.ix, T.iy, T.iz);
                     const float t = (split - o_a) * i_a;
                     const bool below_first = (o_a < split) || (o_a == split && d_a <= 0.f);
-                    const int pair = (int)(packed >> 2);
-                    const int near_n = pair + (below_first ? 0 : 1);
-                    const int far_n = pair + (below_first ? 1 : 0);
-                    if (t > T.tmax || t <= 0.f) T.node = near_n;
-                    else if (t < T.tmin) T.node = far_n;
-                    else {
-                        if (T.sp < kPoolStack) { stk[(size_t)T.sp * kPoolRays] = make_float4(__int_as_float(far_n), t, T.tmax, 0.f); ++T.sp; }
-                        T.node = near_n;
-                        T.tmax = t;
-                    }
+                    const int near_n = (int)hi + (below_first ? 0 : 1);
+                    const int far_n = (int)hi + (below_first ? 1 : 0);
+                    const bool near_only = (t > T.tmax) || (t <= 0.f);
+                    const bool far_only = !near_only && (t < T.tmin);
+                    const bool both = !near_only && !far_only;
+                    if (both && T.sp < kPoolStack) { stk[(unsigned)T.sp * (unsigned)kPoolRays] = make_float4(__int_as_float(far_n), t, T.tmax, 0.f); ++T.sp; }
+                    T.node = far_only ? far_n : near_n;
+                    T.tmax = both ? t : T.tmax;
                 }
                 if (next == 2) {
                     src.done((size_t)(unsigned)e.w, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
                 } else {
-                    sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(T.node), __int_as_float(T.sp | (need_pop ? (1 << 30) : 0)));
+                    sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(T.node), __int_as_float(T.sp | (T.degen ? (1 << 29) : 0) | (need_pop ? (1 << 30) : 0)));
                     if (next == 1) sm.e[slot] = e;
                 }
             }

@@ -125,10 +125,21 @@ WRT_HD float bound_entry(const float4 a, const float4 b, const RayIn& r,
 // kd_traverse() below runs them in a plain loop; the persistent kernels (trace_persistent.cuh) run the
 // SAME steps but let idle lanes of a warp pick up new rays in between.  Either way every ray performs
 // the same arithmetic in the same order.
+// A ray for which a slab product can be NaN: zero / infinite / NaN direction components (invDir infinite, zero or NaN)
+// or a non-finite origin.  Axis-parallel rays are the common case; they keep the guarded test.
+WRT_HD bool ray_is_degenerate(const RayIn& r, float ix, float iy, float iz)
+{
+    const float big = 3.0e38f;
+    const bool inv_ok = fabsf(ix) < big && fabsf(iy) < big && fabsf(iz) < big && ix != 0.f && iy != 0.f && iz != 0.f;
+    const bool org_ok = fabsf(r.ox) < big && fabsf(r.oy) < big && fabsf(r.oz) < big;
+    return !(inv_ok && org_ok);
+}
+
 struct Trav {
     float tmin, tmax, best;
     float ix, iy, iz;     // invDir
     int node, sp, res;
+    bool degen;           // ray_is_degenerate(): keep the NaN-guarded bounds test
 };
 
 struct TravStack {            // KDTodo (KDtreeAccel.h:47-51): one 16-byte entry = one local-memory access
@@ -140,6 +151,7 @@ WRT_HD bool trav_begin(const DevSceneView& sc, const RayIn& r, Trav& T)
     if (!aabb_hit(sc.root_lo, sc.root_hi, r, T.tmin, T.tmax)) return false;     // :311-313
     T.ix = 1.f / r.dx; T.iy = 1.f / r.dy; T.iz = 1.f / r.dz;                     // invDir, :315
     T.node = 0; T.sp = 0; T.res = -1; T.best = WRT_INF;
+    T.degen = ray_is_degenerate(r, T.ix, T.iy, T.iz);
     return true;
 }
 
@@ -165,13 +177,27 @@ WRT_HD void bound_interval(const float4 a, const float4 b, const RayIn& r, float
     box_interval(a.z, a.w, b.x, b.y, b.z, b.w, r, ix, iy, iz, entry, exit_);
 }
 
+// Same interval for a "regular" ray: finite origin, finite non-zero invDir (ray_is_degenerate() == false).  No slab can
+// be NaN then ((finite or +-inf bound - finite) * finite non-zero), so the NaN guards — a third of the instructions of
+// the box test — are dropped; the values computed are identical to box_interval's.
+WRT_HD void box_interval_regular(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayIn& r,
+                                 float ix, float iy, float iz, float& entry, float& exit_)
+{
+    const float x0 = (lox - r.ox) * ix, x1 = (hix - r.ox) * ix;
+    const float y0 = (loy - r.oy) * iy, y1 = (hiy - r.oy) * iy;
+    const float z0 = (loz - r.oz) * iz, z1 = (hiz - r.oz) * iz;
+    entry = fmaxf(fminf(x0, x1), fmaxf(fminf(y0, y1), fminf(z0, z1)));
+    exit_ = fminf(fmaxf(x0, x1), fminf(fmaxf(y0, y1), fmaxf(z0, z1)));
+}
+
 // The PRUNED skip test on an explicit conservative box: nothing inside can change the traversal state when the
 // ray (a) enters the box later than best * (1 + 1e-4) or (b) does not enter it at all / only behind its origin.
 WRT_HD bool box_prunable(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayIn& r,
-                         float ix, float iy, float iz, int res, float best)
+                         float ix, float iy, float iz, int res, float best, bool degenerate)
 {
     float en, ex;
-    box_interval(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz, en, ex);
+    if (degenerate) box_interval(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz, en, ex);
+    else box_interval_regular(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz, en, ex);
     if (res >= 0 && en > best * WRT_PRUNE_REL) return true;
     const float m = 1e-4f * (fabsf(en) + fabsf(ex)) + 1e-4f;
     return (en > ex + m) || (ex < -m);
@@ -189,7 +215,7 @@ WRT_HD bool trav_skip(const DevSceneView& sc, const float4 na, const RayIn& r, c
     // origin): a reported hit lies inside the bounds of its primitive, so nothing below can be hit.
     if (PRUNED) {
         const float4 nb = ldg4(&sc.nodes[2 * T.node + 1]);
-        return box_prunable(na.z, na.w, nb.x, nb.y, nb.z, nb.w, r, T.ix, T.iy, T.iz, T.res, T.best);
+        return box_prunable(na.z, na.w, nb.x, nb.y, nb.z, nb.w, r, T.ix, T.iy, T.iz, T.res, T.best, T.degen);
     }
     return false;
 #else
@@ -274,7 +300,7 @@ WRT_HD void trav_leaf(const DevSceneView& sc, const float4 na, const RayIn& r, T
         if (f2i(r2.w) == WRT_REC_SKIP) {
             if (PRUNED) {
                 if (COUNT) vc->inner++;      // a bounds test, counted with the node visits
-                if (box_prunable(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r, T.ix, T.iy, T.iz, T.res, T.best)) i += f2i(r0.w);
+                if (box_prunable(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r, T.ix, T.iy, T.iz, T.res, T.best, T.degen)) i += f2i(r0.w);
             }
             continue;
         }
