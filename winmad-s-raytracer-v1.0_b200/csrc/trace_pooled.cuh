@@ -177,6 +177,7 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 int4 e = sm.e[slot];
                 T.res = e.x;
                 float4* stk = gstack + slot;                      // entry (sp, slot) at stk[sp * kPoolRays]
+                // (unrolling this loop was measured: by 2 -1.4 %, fully -41 % — instruction cache)
                 for (int s = 0; s < kNodeSteps; s++) {
                     if (need_pop) {
                         need_pop = false;
