@@ -6,6 +6,8 @@
 // traversing, so long and short rays balance inside a warp and across the machine.  One thread = one
 // ray at a time; the per-thread traversal stack lives in local memory (L1-resident, lane-interleaved).
 #include <string>
+#include <cstring>
+#include <cstdlib>
 #include "trace_pooled.cuh"
 #include "warp_utils.cuh"
 
@@ -180,9 +182,15 @@ int persistent_grid_for(const void* kernel, int block)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // traversal is bound by L1TEX: kernels that keep no state in shared memory get the whole unified cache as L1
     cudaFuncAttributes fa;
+    memset(&fa, 0, sizeof fa);
     if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess && fa.sharedSizeBytes == 0)
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    // experiment knobs: fewer resident blocks / an explicit shared-memory carve-out trade occupancy for L1
+    if (fa.sharedSizeBytes != 0) {
+        if (const char* e = getenv("WRT_SMEM_CARVEOUT")) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+    }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+    if (const char* e = getenv("WRT_BLOCKS_PER_SM")) { const int cap = atoi(e); if (cap > 0 && per_sm > cap) per_sm = cap; }
     if (per_sm < 1) per_sm = 1;
     if (per_sm > kMaxBlocksPerSm) per_sm = kMaxBlocksPerSm;   // the traversal scratch is sized for this many
     return sms * per_sm;
