@@ -48,9 +48,11 @@ WORKLOADS = {
 }
 
 
-# DRAM bytes per ray of k_pt_extend from the committed ncu capture (profiles/r1_final_launches_and_ncu.md):
-# (996.3 + 333.3) MB for one 8 388 608-ray launch on C3.
-NCU_DRAM_BYTES_PER_RAY = {"c3": (996.345088e6 + 333.309696e6) / 8388608.0}
+# DRAM bytes per ray of k_pt_extend from the committed ncu captures (profiles/r1_final_launches_and_ncu.md: C3, one
+# 33 554 432-ray launch, dram__bytes_read.sum 4.749 GB + dram__bytes_write.sum 1.546 GB; profiles/r1_ncu_extend_c5.md: C5,
+# one 33 554 432-ray launch, 22.52 GB + 4.88 GB).
+NCU_DRAM_BYTES_PER_RAY = {"c3": (4.749402e9 + 1.546372e9) / 33554432.0, "c5": (22.523734e9 + 4.877666e9) / 33554432.0}
+NCU_SOURCE = {"c3": "profiles/r1_final_launches_and_ncu.md", "c5": "profiles/r1_ncu_extend_c5.md"}
 
 
 def make_scene(w):
@@ -425,7 +427,12 @@ def main():
                             "unit": "GB/s", "frac": achieved / peak,
                             "traffic": (NCU_DRAM_BYTES_PER_RAY.get(args.workload) or 0) * ext_rays / max(ext_launches, 1) or None,
                             "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per ray of one ncu --set full capture "
-                                              "(profiles/r1_final_launches_and_ncu.md) x rays per launch",
+                                              "(%s) x rays per launch" % NCU_SOURCE.get(args.workload, "none for this workload"),
+                            "frac_note": "frac uses the REFERENCE-semantics bytes SURVEY 8(d) defines (full traversal, no early exit); PRUNED traversal "
+                                         "skips most of that work, so frac > 1 is possible and says how much of the reference's traffic is avoided, not a "
+                                         "bandwidth; frac_own_work = the kernels' own algorithmic bytes / peak.  The scene is L2-resident and the "
+                                         "kernel is bound by issue slots and L2 latency (profiles/): DRAM traffic per launch is in `traffic`",
+                            "frac_own_work": (ext_rays * b_ray_k) / (ext_ms * 1e-3) / 1e9 / peak,
                             "bytes_per_ray": b_ray, "visits_per_ray_reference_semantics": visits,
                             "kernel_own_work": {"visits_per_ray": visits_k, "bytes_per_ray": b_ray_k,
                                                 "achieved_GBps": (ext_rays * b_ray_k) / (ext_ms * 1e-3) / 1e9,
