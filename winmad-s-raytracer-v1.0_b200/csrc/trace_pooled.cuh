@@ -179,7 +179,8 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 float4* stk = gstack + slot;                      // entry (sp, slot) at stk[sp * kPoolRays]
                 // (measured and dropped: unrolling this loop by 2 -1.4 %, fully -41 % (instruction cache); prefetch.global.L1
                 //  of the child pair right after the node header is known -19 % / -42 % for one / both children, of a
-                //  leaf's first records on leaf entry -4 %: profiles/r1_experiments.md)
+                //  leaf's first records on leaf entry -4 %; a warp-uniform loop with a `live` flag instead of the breaks -4 %:
+                //  profiles/r1_experiments.md)
                 for (int s = 0; s < kNodeSteps; s++) {
                     if (need_pop) {
                         need_pop = false;
