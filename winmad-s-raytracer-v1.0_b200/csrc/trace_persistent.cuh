@@ -200,8 +200,7 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
                                 const int cnt = (int)(__float_as_uint(na.y) >> 2);
                                 if (cnt > 0) { in_leaf = true; rec = __float_as_int(na.x); rec_end = rec + cnt; }
                                 else need_pop = true;
-                            } else if (PRUNED) trav_interior_prune(sc, na, r, T, S);
-                            else trav_interior(na, r, T, S);
+                            } else trav_interior(na, r, T, S);
                         }
                     }
                     if (finished) { src.done(item, r, T.res, (T.res >= 0) ? T.best : WRT_INF); active = false; }

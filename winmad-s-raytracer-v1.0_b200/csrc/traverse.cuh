@@ -104,19 +104,6 @@ WRT_HD bool sphere_t(float cx, float cy, float cz, float radius, const float lo[
     return true;
 }
 
-// Entry distance of the ray into a conservative box; NaN-safe (a NaN slab never prunes).
-WRT_HD float bound_entry(const float4 a, const float4 b, const RayIn& r,
-                                             float ix, float iy, float iz)
-{
-    float t0 = (a.z - r.ox) * ix, t1 = (b.y - r.ox) * ix;
-    float ex = (t0 != t0 || t1 != t1) ? -HUGE_VALF : fminf(t0, t1);
-    t0 = (a.w - r.oy) * iy; t1 = (b.z - r.oy) * iy;
-    float ey = (t0 != t0 || t1 != t1) ? -HUGE_VALF : fminf(t0, t1);
-    t0 = (b.x - r.oz) * iz; t1 = (b.w - r.oz) * iz;
-    float ez = (t0 != t0 || t1 != t1) ? -HUGE_VALF : fminf(t0, t1);
-    return fmaxf(ex, fmaxf(ey, ez));
-}
-
 #define WRT_PRUNE_REL 1.0001f
 
 // ---- traversal state machine ------------------------------------------------------------------------
@@ -203,28 +190,17 @@ WRT_HD bool box_prunable(float lox, float loy, float loz, float hix, float hiy, 
     return (en > ex + m) || (ex < -m);
 }
 
-#ifndef WRT_MISS_PRUNE
-#define WRT_MISS_PRUNE 1
-#endif
-
+// The PRUNED skip test of a node: its conservative bounds (second half of the 32-byte node) are prunable.
+// (a) alone — skipping only what lies behind the best hit — gave 345 Mrays/s on C3; (b), which also works before any
+// hit is known, 1104 (profiles/r1_experiments.md, "Miss pruning").
 template <bool PRUNED>
 WRT_HD bool trav_skip(const DevSceneView& sc, const float4 na, const RayIn& r, const Trav& T)
 {
-#if WRT_MISS_PRUNE
-    // Also skip a sub-tree whose conservative bounds the ray does not enter at all (or only behind its
-    // origin): a reported hit lies inside the bounds of its primitive, so nothing below can be hit.
     if (PRUNED) {
         const float4 nb = ldg4(&sc.nodes[2 * T.node + 1]);
         return box_prunable(na.z, na.w, nb.x, nb.y, nb.z, nb.w, r, T.ix, T.iy, T.iz, T.res, T.best, T.degen);
     }
     return false;
-#else
-    if (PRUNED && T.res >= 0) {
-        const float4 nb = ldg4(&sc.nodes[2 * T.node + 1]);
-        return bound_entry(na, nb, r, T.ix, T.iy, T.iz) > T.best * WRT_PRUNE_REL;
-    }
-    return false;
-#endif
 }
 
 WRT_HD void trav_interior(const float4 na, const RayIn& r, Trav& T, TravStack& S)
@@ -244,41 +220,6 @@ WRT_HD void trav_interior(const float4 na, const RayIn& r, Trav& T, TravStack& S
     else if (t < T.tmin) T.node = far_n;                                          // :347-348
     else {                                                                        // :349-357
         if (T.sp < WRT_STACK_DEPTH) { S.e[T.sp] = make_float4(i2f(far_n), t, T.tmax, 0.f); ++T.sp; }
-        T.node = near_n;
-        T.tmax = t;
-    }
-}
-
-// PRUNED traversal only: same step as trav_interior, but a far child whose conservative bounds already
-// fail the prune test is not pushed at all.  `best` only ever decreases, so a sub-tree that is prunable
-// now is prunable when it would have been popped: dropping it here removes a push, a pop and a node
-// fetch without changing any state the reference would have.  The far child is the near child's
-// neighbour in memory (sibling pairs are adjacent), so its bounds share the cache line fetched next.
-WRT_HD void trav_interior_prune(const DevSceneView& sc, const float4 na, const RayIn& r, Trav& T, TravStack& S)
-{
-    const unsigned packed = f2u(na.y);
-    const int axis = (int)(packed & 3u);
-    const float split = na.x;
-    const float o_a = sel3(axis, r.ox, r.oy, r.oz);
-    const float d_a = sel3(axis, r.dx, r.dy, r.dz);
-    const float i_a = sel3(axis, T.ix, T.iy, T.iz);
-    const float t = (split - o_a) * i_a;
-    const bool below_first = (o_a < split) || (o_a == split && d_a <= 0.f);
-    const int pair = (int)(packed >> 2);
-    const int near_n = pair + (below_first ? 0 : 1);
-    const int far_n = pair + (below_first ? 1 : 0);
-    if (t > T.tmax || t <= 0.f) T.node = near_n;
-    else if (t < T.tmin) T.node = far_n;
-    else {
-        bool push = true;
-#ifndef WRT_PREPUSH
-#define WRT_PREPUSH 0   /* measured: no gain on C3, -1..2 % on torus / cbox (profiles/r1_experiments.md) */
-#endif
-        if (WRT_PREPUSH && T.res >= 0) {
-            const float4 fa = ldg4(&sc.nodes[2 * far_n]), fb = ldg4(&sc.nodes[2 * far_n + 1]);
-            push = !(bound_entry(fa, fb, r, T.ix, T.iy, T.iz) > T.best * WRT_PRUNE_REL);
-        }
-        if (push && T.sp < WRT_STACK_DEPTH) { S.e[T.sp] = make_float4(i2f(far_n), t, T.tmax, 0.f); ++T.sp; }
         T.node = near_n;
         T.tmax = t;
     }
@@ -339,7 +280,7 @@ WRT_HD int kd_traverse(const DevSceneView& sc, const RayIn& r, float& best_t, Vi
         if (!trav_skip<PRUNED>(sc, na, r, T)) {
             if ((f2u(na.y) & 3u) != WRT_LEAF_TAG) {
                 if (COUNT) vc->inner++;
-                if (PRUNED) trav_interior_prune(sc, na, r, T, S); else trav_interior(na, r, T, S);
+                trav_interior(na, r, T, S);
                 continue;
             }
             if (COUNT) vc->leaf++;
