@@ -13,10 +13,11 @@
 // std::max/std::min/std::swap are spelled out as the comparisons they perform so that NaNs (0*inf
 // from axis-parallel rays) take the same branches as on the CPU.
 //
-// PRUNED mode keeps the visit order but skips a sub-tree when a conservative bound of everything
-// referenced below it (DevNode bounds, built by scene_upload.cu) is entered by the ray later than
-// best*(1+1e-4): no hit there can satisfy `t < best - EPS`, so skipping never changes the state the
-// reference would have.  tests/test_traversal_gpu.py checks EXACT == PRUNED ray for ray.
+// PRUNED mode keeps the visit order but skips a sub-tree — or a chunk of a leaf's records (skip records) —
+// when a conservative bound of everything referenced in it (built by scene_layout.cpp) is entered by the ray
+// later than best*(1+1e-4), or is not entered at all: no hit there can satisfy `t < best - EPS` / exist, so
+// skipping never changes the state the reference would have (box_prunable).  tests/test_gpu_traversal.py and
+// tests/test_hostsim.py check EXACT == PRUNED == oracle ray for ray.
 #pragma once
 #include "dev_scene.h"
 
