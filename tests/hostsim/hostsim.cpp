@@ -215,6 +215,7 @@ void hs_render_bdpt(void* hv, const wrt_camera* cam, const wrt_bdpt_params* p, i
     P.control_len = p->control_length; P.seed = p->seed;
     P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->iterations;
     P.n_paths = (unsigned)(p->width * p->height); P.light_path_num = (float)(p->width * p->height);
+    P.n_pixels = P.n_paths; P.iter_stride = 1;      // one iteration at a time here; the kernels batch several
     P.trace_gated = 1;
     const int stride = p->iter_stride > 0 ? p->iter_stride : 1;
     const int maxv = P.max_len > 1 ? P.max_len - 1 : 1;

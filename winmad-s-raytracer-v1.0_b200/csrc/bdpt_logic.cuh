@@ -26,10 +26,12 @@ struct BdptParams {
     int width, height;
     int min_len, max_len, control_len;
     uint32_t seed;
-    int iteration;            // global iteration index: keys the RNG streams
+    int iteration;            // global index of the first iteration of this batch: keys the RNG streams
+    int iter_stride;          // path slot i belongs to iteration `iteration + (i / n_pixels) * iter_stride`, pixel i % n_pixels
     float film_scale;
     float light_path_num;     // lightPathNum = width * height
-    unsigned n_paths;
+    unsigned n_pixels;        // width * height: paths per iteration
+    unsigned n_paths;         // path slots of this batch = (iterations in the batch) * n_pixels
     int trace_gated;          // 1: also trace connection rays whose contribution is gated out (as the reference does)
 };
 
@@ -68,7 +70,11 @@ WRT_HD V3 cdiv(V3 c, float s) { return v3(c.x / s, c.y / s, c.z / s); }   // Col
 // generateLightSample + the first Ray(origin + dir*EPS, dir) of the light loop (:73-80)
 WRT_HD void bdpt_light_generate(const DevSceneView& sc, const BdptParams& P, uint32_t index, RayIn& ray, BdptPath& st)
 {
-    st.rng = rng_make(P.seed, 1u, (unsigned long long)P.iteration * P.n_paths + index);
+    // several iterations run side by side (the reference runs them one after the other; they are independent: camera
+    // path p only reads light path p of its own iteration, bidirPathTracing.cpp:222-229)
+    const uint32_t within = index % P.n_pixels;
+    const unsigned long long iter = (unsigned long long)P.iteration + (unsigned long long)(index / P.n_pixels) * (unsigned)P.iter_stride;
+    st.rng = rng_make(P.seed, 1u, iter * P.n_pixels + within);
     const int nl = sc.n_lights;
     const float pick = 1.f / nl;
     int lid = (int)(rng_float(st.rng) * nl);
@@ -92,8 +98,10 @@ WRT_HD void bdpt_light_generate(const DevSceneView& sc, const BdptParams& P, uin
 // generateCameraSample + the first Ray(origin + dir*EPS, dir) of the camera loop (:147-149)
 WRT_HD void bdpt_camera_generate(const BdptParams& P, const DevCamera& cam, uint32_t index, RayIn& ray, BdptPath& st)
 {
-    st.rng = rng_make(P.seed, 2u, (unsigned long long)P.iteration * P.n_paths + index);
-    const int y = (int)(index % (uint32_t)P.width), x = (int)(index / (uint32_t)P.width);
+    const uint32_t within = index % P.n_pixels;
+    const unsigned long long iter = (unsigned long long)P.iteration + (unsigned long long)(index / P.n_pixels) * (unsigned)P.iter_stride;
+    st.rng = rng_make(P.seed, 2u, iter * P.n_pixels + within);
+    const int y = (int)(within % (uint32_t)P.width), x = (int)(within / (uint32_t)P.width);
     const V3 j = rng_vec3(st.rng);
     const float sx = (float)x + j.x, sy = (float)y + j.y;
     RayIn cr;

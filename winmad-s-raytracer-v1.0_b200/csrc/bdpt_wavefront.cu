@@ -251,6 +251,20 @@ static int bdpt_buffers(wrt_wavefront* wf, unsigned n_paths, int maxv, BdptBuffe
     return WRT_OK;
 }
 
+// Iterations are independent, so several run side by side in one wavefront: launches become `batch` times larger and
+// `batch` times fewer (at 1440 x 1440 one iteration is only 2 M paths and ~60 sub-millisecond launches with a host round
+// trip each).  Batch = as many iterations as fit 2^24 path slots (knob: WRT_BDPT_BATCH_PATHS).
+static int bdpt_batch(const wrt_bdpt_params* p)
+{
+    const int stride = p->iter_stride > 0 ? p->iter_stride : 1;
+    const int my_iters = std::max(1, (p->iterations - p->iter_first + stride - 1) / stride);
+    unsigned long long slot_budget = 1ull << 24;
+    if (const char* e = getenv("WRT_BDPT_BATCH_PATHS")) slot_budget = (unsigned long long)atoll(e);
+    const unsigned long long npix = (unsigned long long)p->width * p->height;
+    const int batch = (int)std::max<unsigned long long>(1ull, slot_budget / std::max<unsigned long long>(npix, 1ull));
+    return std::min(batch, my_iters);
+}
+
 static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* d_film, cudaStream_t st)
 {
     if (!cam || !p || p->width <= 0 || p->height <= 0 || p->iterations <= 0 || p->max_path_length < 1) {
@@ -266,19 +280,25 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
     P.width = p->width; P.height = p->height; P.min_len = p->min_path_length; P.max_len = p->max_path_length;
     P.control_len = p->control_length; P.seed = p->seed; P.iteration = 0;
     P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->iterations;
-    P.n_paths = (unsigned)(p->width * p->height);
+    P.n_pixels = (unsigned)(p->width * p->height);
+    P.n_paths = P.n_pixels;
     P.light_path_num = (float)(p->width * p->height);
     { const char* e = getenv("WRT_BDPT_SKIP_GATED"); P.trace_gated = (e && atoi(e)) ? 0 : 1; }
     const int stride = p->iter_stride > 0 ? p->iter_stride : 1;
     if (p->iter_first < 0 || p->iter_first >= p->iterations) { set_error("wrt_render_bdpt: iter_first out of range"); return WRT_ERR_INVALID; }
+    P.iter_stride = stride;
     const int maxv = std::max(P.max_len - 1, 1);
     DevCamera dc; fill_camera(cam, dc);
 
+    const int my_iters = (p->iterations - p->iter_first + stride - 1) / stride;
+    const int batch = bdpt_batch(p);
+    const unsigned max_slots = P.n_pixels * (unsigned)batch;
+
     wrt_wavefront* wf = nullptr;
-    int rc = wavefront_get(sc, (int)std::max(P.n_paths, 1024u), &wf);
+    int rc = wavefront_get(sc, (int)std::max(max_slots, 1024u), &wf);
     if (rc) return rc;
     BdptBuffers* B = nullptr;
-    rc = bdpt_buffers(wf, P.n_paths, maxv, &B);
+    rc = bdpt_buffers(wf, max_slots, maxv, &B);
     if (rc) return rc;
     BdptBuffers Bv = *B;
     Bv.n_paths = B->n_paths;      // stride of the vertex array
@@ -306,8 +326,10 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
     sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
     WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
 
-    for (int it = p->iter_first; it < p->iterations; it += stride) {
-        P.iteration = it;
+    for (int done_iters = 0; done_iters < my_iters; done_iters += batch) {
+        const int nb = std::min(batch, my_iters - done_iters);
+        P.iteration = p->iter_first + done_iters * stride;
+        P.n_paths = P.n_pixels * (unsigned)nb;
         for (int phase = 0; phase < 2; phase++) {
             if (phase == 0) k_bdpt_light_init<<<g_li, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[0]);
             else k_bdpt_camera_init<<<g_ci, kBlock, 0, st>>>(P, dc, wf->pool, Bv, wf->queue[0]);
@@ -392,7 +414,7 @@ int wrt_render_bdpt(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params*
         set_error("wrt_render_bdpt: the film must be square and non-empty (bidirPathTracing.cpp:29-45)"); return WRT_ERR_INVALID;
     }
     wrt_wavefront* wf = nullptr;
-    int rc = wavefront_get(sc, std::max(p->width * p->height, 1024), &wf);   // grow the pool first (frees the film)
+    int rc = wavefront_get(sc, std::max(p->width * p->height * bdpt_batch(p), 1024), &wf);   // grow the pool first (frees the film)
     if (rc) return rc;
     const size_t floats = (size_t)p->width * p->height * 3;
     float* d_film = nullptr;
