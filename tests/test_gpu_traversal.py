@@ -158,6 +158,48 @@ def test_headline_scene_against_oracle_port(wrt):
     assert np.array_equal(e[0], f[0]) and np.array_equal(util.bits(e[1]), util.bits(f[1]))
 
 
+def test_c5_class_scene_against_oracle_port_and_exact(wrt):
+    """C5's generator at 1/5 scale (2 000 000 triangles + 20 000 spheres: long leaves, skip records with groups, sphere
+    records): CUDA PRUNED == oracle port on a sample the port finishes in seconds, and PRUNED == EXACT on 4K-frame
+    primary + secondary batches."""
+    sc = scenes.synthetic_torus_scene(n=1000, width=3840, height=2160, n_spheres=20000)
+    port = engines.PortEngine(wrt, sc)
+    scene = wrt.Scene(port.hs)
+    cam = port.hs.camera()
+    rays = wrt.generate_rays(cam, scenes.pixel_centres(3840, 2160, step=24) + np.float32(0.41))
+    a = scene.intersect(rays, full=True); b = port.intersect(rays, full=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(util.bits(a[1]), util.bits(b[1]))
+    hit = a[0] >= 0
+    r2 = wrt.make_rays(scenes.bounce_rays(a[2], a[3], hit))
+    c, d = scene.intersect(r2), port.intersect(r2)
+    assert np.array_equal(c[0], d[0]) and np.array_equal(util.bits(c[1]), util.bits(d[1]))
+    # rays aimed at sphere centres from the camera and from the opposite side.  Reference quirk: Sphere::hit rejects
+    # t_hc = r^2 - d_perp^2 unless it exceeds EPS = 1e-3 (sphere.cpp:44-46), so spheres with r < 0.0316 — all of C5's —
+    # can never be hit; they still cost their tests.  Both sides must agree on exactly that.
+    cen = sc.data[sc.kind == 1][:4000, 0:3]
+    o1 = np.broadcast_to(sc.cam12[0:3].astype(np.float32), cen.shape)
+    o2 = (2 * cen.mean(0) - sc.cam12[0:3]).astype(np.float32)[None, :] + np.zeros_like(cen)
+    aim = wrt.make_rays(np.concatenate([np.concatenate([o1, cen - o1], 1), np.concatenate([o2, cen - o2], 1)]).astype(np.float32))
+    g, h = scene.intersect(aim), port.intersect(aim)
+    assert np.array_equal(g[0], h[0]) and np.array_equal(util.bits(g[1]), util.bits(h[1]))
+    assert (sc.kind[g[0][g[0] >= 0]] == 1).sum() == 0 and float(sc.data[sc.kind == 1][:, 3].max()) < 0.0316
+    q = scenes.nee_queries(a[2], hit & (a[5] > 0), sc.lights)
+    assert np.array_equal(scene.occluded(q), port.occluded(q))
+    adv = wrt.make_rays(engines.adversarial_rays(sc, 6000))
+    e, f = scene.intersect(adv), port.intersect(adv)
+    assert np.array_equal(e[0], f[0]) and np.array_equal(util.bits(e[1]), util.bits(f[1]))
+    # size-independent property at the full frame: PRUNED (pooled scheduler, skip records) == EXACT
+    big = wrt.generate_rays(cam, scenes.pixel_centres(3840, 2160, step=2))
+    p1 = scene.intersect(big, full=True)
+    big2 = wrt.make_rays(scenes.bounce_rays(p1[2], p1[3], p1[0] >= 0))
+    scene.set_traversal(wrt.TRAVERSE_EXACT)
+    x1 = scene.intersect(big); x2 = scene.intersect(big2)
+    scene.set_traversal(wrt.TRAVERSE_PRUNED)
+    p2 = scene.intersect(big2)
+    assert np.array_equal(p1[0], x1[0]) and np.array_equal(util.bits(p1[1]), util.bits(x1[1]))
+    assert np.array_equal(p2[0], x2[0]) and np.array_equal(util.bits(p2[1]), util.bits(x2[1]))
+
+
 def test_visit_counters_and_stats(wrt):
     sc, z = scenes.load_fixture("torus")
     cuda = engines.CudaEngine(wrt, sc, True); port = engines.PortEngine(wrt, sc)
