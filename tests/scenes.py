@@ -212,3 +212,39 @@ def bounce_rays(p, n, mask, salt=7):
     d = (hn + s).astype(np.float32)
     o = (hp + d * f(1e-3)).astype(np.float32)
     return np.concatenate([o, d], 1).astype(np.float32)
+
+
+# ---- .scene + OBJ files in the reference's format (for the loader / CLI tests) -----------------------------
+def write_scene_files(sc, out_dir, name="scene"):
+    """Writes `sc` (triangles only) as <out_dir>/<name>.scene plus one OBJ per material and one for the light
+    (format of R/torus.scene; loaded by Scene::loadScene and by our host/scene_io.cpp).  Returns the scene path."""
+    import os
+    assert (sc.kind == 0).all(), "the .scene format of the reference has no sphere element"
+    def obj(path, tris):
+        with open(path, "w") as f:
+            for t in tris.reshape(-1, 3):
+                f.write("v %.9g %.9g %.9g\n" % tuple(float(x) for x in t))
+            for k in range(len(tris)):
+                f.write("f %d %d %d\n" % (3 * k + 1, 3 * k + 2, 3 * k + 3))
+    xml = ["<scene>", "<camera>",
+           '<position x="%.9g" y="%.9g" z="%.9g"/>' % tuple(float(x) for x in sc.cam12[0:3]),
+           '<forward x="%.9g" y="%.9g" z="%.9g"/>' % tuple(float(x) for x in sc.cam12[3:6]),
+           '<up x="%.9g" y="%.9g" z="%.9g"/>' % tuple(float(x) for x in sc.cam12[6:9]),
+           '<resolution height="%d" width="%d"/>' % (int(sc.cam12[9]), int(sc.cam12[10])),   # the loader swaps the two (scene.cpp:292-295)
+           '<horizontalFOV horizontalFOV="%.9g"/>' % float(sc.cam12[11]), "</camera>"]
+    for m in np.asarray(sc.materials, np.float32).reshape(-1, 11):
+        xml.append('<material><diffuse r="%.9g" g="%.9g" b="%.9g"/><glossy r="%.9g" g="%.9g" b="%.9g"/>'
+                   '<specular r="%.9g" g="%.9g" b="%.9g"/><phongExp phongExp="%.9g"/><refracIndex refracIndex="%.9g"/></material>'
+                   % (m[0], m[1], m[2], m[3], m[4], m[5], m[7], m[8], m[9], m[6], m[10]))
+    for mid in sorted(set(int(x) for x in sc.matid if x > 0)):
+        path = os.path.join(out_dir, "%s_mat%d.obj" % (name, mid))
+        obj(path, sc.data[sc.matid == mid])
+        xml.append('<object><file_path path="%s"/><matid matid="%d"/></object>' % (path, mid))
+    lpath = os.path.join(out_dir, "%s_light.obj" % name)
+    obj(lpath, sc.data[sc.matid < 0])
+    inten = np.asarray(sc.lights, np.float32).reshape(-1, 12)[0, 9:12]
+    xml.append('<area_light><file_path path="%s"/><intensity r="%.9g" g="%.9g" b="%.9g"/></area_light>' % (lpath, inten[0], inten[1], inten[2]))
+    xml.append("</scene>")
+    spath = os.path.join(out_dir, name + ".scene")
+    open(spath, "w").write("\n".join(xml) + "\n")
+    return spath

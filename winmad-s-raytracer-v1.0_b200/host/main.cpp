@@ -1,6 +1,6 @@
 // wrt_tot — the reference's command line for the two integrators this repository replaces:
 //
-//     wrt_tot <scene file> <output image (.ppm / .bmp)> -p | -bpt [parameters.para]
+//     wrt_tot <scene file> <output image (.ppm / .bmp)> -p | -r | -bpt [parameters.para]
 //
 // mirrors `ToT <scene> <image> <mode>` (R/src/main.cpp:29-97) for mode -p (PathIntegrator) and -bpt
 // (BidirPathTracing): loads `src/parameters.para` (or the given file) exactly like
@@ -44,7 +44,7 @@ static int fail(const char* what)
 int main(int argc, char* argv[])
 {
     if (argc < 4) {
-        fprintf(stderr, "usage: %s <scene> <image.ppm|.bmp> -p|-bpt [parameters.para]\n", argv[0]);
+        fprintf(stderr, "usage: %s <scene> <image.ppm|.bmp> -p|-r|-bpt [parameters.para]\n", argv[0]);
         return 2;
     }
     Parameters para;
