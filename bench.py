@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("WRT_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (PT) / iterations (BDPT)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every GPU renders the workload's spp; strong: the spp (iterations) are sharded over the GPUs "
+                         "(samples k = rank, rank + N, ... of the same stratification grid, SURVEY.md 8e)")
     args = ap.parse_args()
 
     w = dict(WORKLOADS[args.workload])
@@ -284,7 +287,13 @@ def main():
         spp = w["spp"]
         whitted = w["integrator"] == "whitted"
 
+        strong = args.scaling == "strong" and world > 1
+        if strong and spp < world:
+            raise SystemExit("bench.py: --scaling strong needs at least one sample per pixel per GPU")
+
         def params(scale):
+            if strong:      # one image: rank g renders samples g, g + N, ... of the shared grid with the shared seed
+                return W.shard_pt(W.PtParams(w["width"], w["height"], spp, w["depth"], 1000, 0, 1, 0.0), rank, world)
             return W.PtParams(w["width"], w["height"], spp, w["depth"], 1000 + rank, 0, 1, scale)
 
         def render_dev(film):
@@ -294,11 +303,17 @@ def main():
 
         def render_host(buf):
             (scene.render_whitted if whitted else scene.render_pt)(cam, params(0.0), buf)
-        samples_per_step = npix * spp
+        samples_per_step = npix * spp if not strong else npix * spp / world
     else:
         iters = w["iterations"]
 
+        strong = args.scaling == "strong" and world > 1
+        if strong and iters < world:
+            raise SystemExit("bench.py: --scaling strong needs at least one iteration per GPU")
+
         def params(scale):
+            if strong:
+                return W.shard_bdpt(W.BdptParams(w["width"], w["height"], iters, 0, 10, 3, 1000, 0, 1, 0.0, 0), rank, world)
             return W.BdptParams(w["width"], w["height"], iters, 0, 10, 3, 1000 + rank, 0, 1, scale, 0)
 
         def render_dev(film):
@@ -307,7 +322,7 @@ def main():
 
         def render_host(buf):
             scene.render_bdpt(cam, params(0.0), buf)
-        samples_per_step = npix * iters
+        samples_per_step = npix * iters if not strong else npix * iters / world
 
     film = torch.zeros((w["height"], w["width"], 3), dtype=torch.float32, device="cuda")
     host_film_t = torch.empty((w["height"], w["width"], 3), dtype=torch.float32, pin_memory=True)
@@ -376,7 +391,7 @@ def main():
     for _ in range(args.steps):
         render_host(host_film)
         if dist is not None:   # host path at N>1: stage through the device film of rank 0
-            film.copy_(host_film_t, non_blocking=True); film.mul_(1.0 / world); dist.reduce(film, 0)
+            film.copy_(host_film_t, non_blocking=True); film.mul_(1.0 if strong else 1.0 / world); dist.reduce(film, 0)
             if rank == 0:
                 host_film_t.copy_(film)
     barrier()
@@ -396,10 +411,11 @@ def main():
     total_samples = samples_per_step * args.steps * world
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["desc"], "integrator": w["integrator"], "traversal": "pruned (bit-exact vs exact, tests/test_gpu_traversal.py)",
-                   "per_gpu": "full frame, %d %s per GPU, disjoint RNG streams; films summed by one NCCL reduce" %
+                   "per_gpu": ("full frame, %d %s per GPU, disjoint RNG streams; films summed by one NCCL reduce" if not strong else
+                               "full frame, %d %s in total, dealt round-robin to the GPUs (same grid and seed as 1 GPU); films summed by one NCCL reduce") %
                               (w.get("spp", w.get("iterations")), "iterations" if w["integrator"] == "bdpt" else "spp"),
                    "l2": "inputs larger than L2: the path pool (2^24 slots x 176 B in 2 concurrent sub-pools) is rewritten every bounce; the scene is meant to stay L2-resident",
                    "prims": int(sc.n_prims), "kd_build_s": round(kd_build_s, 2), "upload_s": round(upload_s, 2)},
