@@ -4,7 +4,8 @@ Run in the build container (needs /root/reference and oracle/_ref/libwrt_ref.so)
 
     python tests/golden/make_golden.py
 
-For each bundled scene it stores, in tests/golden/<name>.npz:
+For each bundled scene and for one programmatic triangle + sphere scene it stores, in
+tests/golden/<name>.npz:
   * the scene as arrays exactly as the reference's loader produced them (Scene::objs order),
     materials, AreaLight constructor arguments, Camera::setup arguments and the camera matrices;
   * a SHA-256 of the reference's flattened KD-tree (topology, split planes, leaf lists);
@@ -66,9 +67,14 @@ def bunny_light_obj(tmp):
     return p
 
 
-def make(name, scene_file):
+def make(name, scene_file=None, arrays=None):
+    """scene_file: a .scene the reference's own loader reads; arrays: a tests/scenes.py SceneArrays built through the
+    same constructor calls the loader makes (ref_build_scene) — the only way to get spheres into a Scene."""
     ref = refpy.RefScene("pt")
-    n = ref.load_file(scene_file, 512, 512)
+    if arrays is not None:
+        n = ref.build(arrays.materials, arrays.kind, arrays.data, arrays.matid, arrays.lights, arrays.cam12, 512, 512)
+    else:
+        n = ref.load_file(scene_file, 512, 512)
     kind, data, matid = ref.prims()
     cam = ref.camera()
     lights22 = ref.lights()
@@ -79,7 +85,9 @@ def make(name, scene_file):
     assert len(em) == len(lights22)
     tr = ref.tree()
     out = dict(kind=kind, data=data, matid=matid, materials=ref.materials(), lights=lights12,
-               cam12=cam[:12].copy(), cam45=cam, width=512, height=512,
+               # Camera::setup does not store its FOV argument (the loader sets the member separately), so for a
+               # programmatic scene the arguments themselves are kept
+               cam12=(cam[:12].copy() if arrays is None else np.asarray(arrays.cam12, np.float32).copy()), cam45=cam, width=512, height=512,
                tree_sha=tree_digest(tr), tree_nodes=len(tr["axis"]), tree_refs=len(tr["refs"]),
                tree_depth=tr["depth"], root_box=tr["box"][0], scene_sphere=ref.scene_sphere())
     xy = scenes.pixel_centres(512, 512, step=2)
@@ -118,6 +126,8 @@ def main():
     xml = scene_xml(cam, 512, 40.0, bunny_mats, [("bunny.obj", 1)], bunny_light_obj(tmp), (60, 60, 60))
     p = os.path.join(tmp, "bunny.scene"); open(p, "w").write(xml)
     make("bunny", p)
+    # triangles AND spheres (a glass and a mirror one among them, radii 0.18-0.25: hittable, unlike C5's): pins Sphere::hit
+    make("small_mixed", arrays=scenes.small_mixed_scene(512, 512))
     # keep the generated scene files next to the fixtures' provenance (tiny, text)
     for f in ("cbox_dragon.scene", "bunny.scene"):
         txt = open(os.path.join(tmp, f)).read().replace(tmp, "$TMP")

@@ -9,7 +9,7 @@ import scenes
 import util
 
 pytestmark = pytest.mark.gpu
-FIXTURES = ["torus", "cbox_dragon", "bunny"]
+FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed"]
 
 
 @pytest.mark.parametrize("pruned", [False, True])

@@ -10,7 +10,7 @@ import pytest
 import scenes
 import util
 
-FIXTURES = ["torus", "cbox_dragon", "bunny"]
+FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed"]
 
 
 @pytest.mark.parametrize("name", FIXTURES)

@@ -8,7 +8,7 @@ import engines
 import scenes
 import util
 
-FIXTURES = ["torus", "cbox_dragon", "bunny"]
+FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed"]
 
 
 @pytest.mark.parametrize("name", FIXTURES)
