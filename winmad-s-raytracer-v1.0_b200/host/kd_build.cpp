@@ -20,6 +20,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <future>
 #include <thread>
 #include "host_scene.h"
@@ -314,6 +316,9 @@ bool build_kdtree(HostScene& hs, std::string& err)
             e[2 * (size_t)j + 1].type = kEnd; e[2 * (size_t)j + 1].pos = boxes[6 * (size_t)j + 3 + a]; e[2 * (size_t)j + 1].index = j;
         }
     }
+    const bool profile = getenv("WRT_KD_PROFILE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     {   // libc qsort on purpose: the comparator is not a strict weak order, so the result depends on
         // the sorting algorithm; the reference's tree is whatever libc qsort makes of it.  The three arrays are
         // independent, so they are sorted concurrently.
@@ -321,6 +326,8 @@ bool build_kdtree(HostScene& hs, std::string& err)
         if (threads > 1) { std::thread t1(sort_axis, 1), t2(sort_axis, 2); sort_axis(0); t1.join(); t2.join(); }
         else for (int a = 0; a < 3; a++) sort_axis(a);
     }
+    if (profile) fprintf(stderr, "[kd] events + sort: %.2f s\n", since(t_start));
+    const auto t_build = std::chrono::steady_clock::now();
     for (int a = 0; a < 3; a++) {
         root->lo[a] = root->ev[a].front().pos;
         root->hi[a] = root->ev[a].back().pos;
@@ -336,6 +343,7 @@ bool build_kdtree(HostScene& hs, std::string& err)
         b.build(root, 1, hs.tree);
     }
     hs.tree_built = true;
+    if (profile) fprintf(stderr, "[kd] build: %.2f s (%d threads), %zu nodes\n", since(t_build), threads, hs.tree.axis.size());
 
     // sceneSphere, scene.cpp:481-487
     const float* rb = hs.tree.root_box;
