@@ -128,6 +128,7 @@ def main():
     make("bunny", p)
     # triangles AND spheres (a glass and a mirror one among them, radii 0.18-0.25: hittable, unlike C5's): pins Sphere::hit
     make("small_mixed", arrays=scenes.small_mixed_scene(512, 512))
+    make("mixed_torus", arrays=scenes.mixed_torus_scene(512, 512))
     # keep the generated scene files next to the fixtures' provenance (tiny, text)
     for f in ("cbox_dragon.scene", "bunny.scene"):
         txt = open(os.path.join(tmp, f)).read().replace(tmp, "$TMP")

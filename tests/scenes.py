@@ -62,7 +62,7 @@ def displaced_torus(n, R=1.0):
     return np.concatenate([t1, t2]).astype(np.float32)
 
 
-def synthetic_torus_scene(n=708, width=1920, height=1080, n_spheres=0, seed=1, name=None, floor=False):
+def synthetic_torus_scene(n=708, width=1920, height=1080, n_spheres=0, seed=1, name=None, floor=False, sphere_radius=None):
     """C3 (n=708 -> 1 002 528 triangles) / C5 (n=2237 + 100k spheres) of SURVEY.md §8d: the displaced
     torus, one diffuse material, a 2-triangle area light above, optional random spheres.  `floor=True`
     adds a 2-triangle ground quad; the reference's SAH builder degenerates into x-slabs with such huge
@@ -85,6 +85,8 @@ def synthetic_torus_scene(n=708, width=1920, height=1080, n_spheres=0, seed=1, n
         ext = tris.reshape(-1, 3).max(0) - tris.reshape(-1, 3).min(0)
         scene_r = 0.5 * float(np.linalg.norm(ext))             # radius of the mesh's bounding sphere (~2.0)
         rad = scene_r * 10 ** (-3 + rng.random(n_spheres))     # log-uniform in [1e-3, 1e-2] * scene radius
+        if sphere_radius is not None:                           # absolute radii (the default ones are below the reference's
+            rad = sphere_radius[0] + (sphere_radius[1] - sphere_radius[0]) * rng.random(n_spheres)   # hittable size, sphere.cpp:44-46)
         sph = np.zeros((n_spheres, 9), np.float32)
         sph[:, :3] = c; sph[:, 3] = rad
         data = np.concatenate([data, sph]); kind = np.concatenate([kind, np.ones(n_spheres, np.int32)])
@@ -143,6 +145,12 @@ def cornell_box_scene(width=512, height=512, closed=True, name="cornell"):
                  material(diffuse=(0.80, 0.15, 0.15)), material(diffuse=(0.1, 0.1, 0.1), phong=(0.7, 0.7, 0.7), phong_exp=90.0)]
     cam12 = np.array([0, -0.98, 0, 0, 1, 0, 0, 0, 1, width, height, 90.0], np.float32)
     return SceneArrays(name, kind, data, matid, materials, lights, cam12, width, height)
+
+
+def mixed_torus_scene(width=512, height=512):
+    """3 200-triangle displaced torus + 200 spheres large enough to be hit (r in [0.05, 0.15]): a tree of > 512 nodes, so
+    the GPU runs its pooled scheduler, with sphere records and skip records in the leaves.  Golden fixture `mixed_torus`."""
+    return synthetic_torus_scene(n=40, width=width, height=height, n_spheres=200, sphere_radius=(0.05, 0.15), name="mixed_torus")
 
 
 def small_mixed_scene(width=64, height=64):

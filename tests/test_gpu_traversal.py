@@ -9,7 +9,7 @@ import scenes
 import util
 
 pytestmark = pytest.mark.gpu
-FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed"]
+FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed", "mixed_torus"]
 
 
 @pytest.mark.parametrize("pruned", [False, True])

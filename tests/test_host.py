@@ -10,7 +10,7 @@ import pytest
 import scenes
 import util
 
-FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed"]
+FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed", "mixed_torus"]
 
 
 @pytest.mark.parametrize("name", FIXTURES)

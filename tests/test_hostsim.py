@@ -10,7 +10,7 @@ import util
 
 
 @pytest.mark.parametrize("pruned", [False, True])
-@pytest.mark.parametrize("name", ["torus", "cbox_dragon", "bunny", "small_mixed"])
+@pytest.mark.parametrize("name", ["torus", "cbox_dragon", "bunny", "small_mixed", "mixed_torus"])
 def test_hostsim_matches_golden(wrt, name, pruned):
     sc, z = scenes.load_fixture(name)
     engines.check_against_golden(wrt, engines.HostSimEngine(wrt, sc, pruned), sc, z)

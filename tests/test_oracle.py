@@ -8,7 +8,7 @@ import engines
 import scenes
 import util
 
-FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed"]
+FIXTURES = ["torus", "cbox_dragon", "bunny", "small_mixed", "mixed_torus"]
 
 
 @pytest.mark.parametrize("name", FIXTURES)
