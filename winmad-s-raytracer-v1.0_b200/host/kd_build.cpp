@@ -249,7 +249,12 @@ struct Builder {
         if (levels <= 0 || nd->objs.size() < 4096) { build(nd, dep, out); return; }
         int axis; Real split; BuildNode* l; BuildNode* r;
         const int n = (int)nd->objs.size();
-        if (!split_node(nd, dep, axis, split, l, r)) {
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool ok = split_node(nd, dep, axis, split, l, r);
+        if (dep <= 3 && getenv("WRT_KD_PROFILE"))
+            fprintf(stderr, "[kd] split at depth %d, %d objects: %.2f s\n", dep, n,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        if (!ok) {
             emit_leaf(out, *nd, dep);
             delete nd;
             return;
