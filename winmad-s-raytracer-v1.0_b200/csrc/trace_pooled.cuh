@@ -1,11 +1,12 @@
 // Pooled traversal (scheduler 3): a warp owns a pool of kPoolRays rays whose traversal state lives in
 // shared memory, and three FIFO rings of slot ids — rays waiting for a node visit, rays waiting for
 // primitive tests, free slots.  Each round the warp serves the longer ring: lane l takes the l-th
-// waiting ray, loads its state (a few LDS.128), performs one unit of work (<= kNodeSteps node visits or
-// <= kPrimSteps leaf records) and re-queues the ray on the ring it now belongs to (ballot/popc
-// positions).  Because there are twice as many rays as lanes, both kinds of round normally run with all
-// 32 lanes, instead of ~40 % of them when every lane is married to one ray (profiles/r1_ncu_extend_*).
-// Free slots are refilled from the global work counter in batches.
+// waiting ray, loads its state (a few LDS.128), performs one unit of work (<= kNodeSteps = 6 node visits or
+// <= kPrimSteps = 4 leaf records, skip records included) and re-queues the ray on the ring it now belongs to
+// (ballot/popc positions).  Because there are twice as many rays as lanes, rounds start with most lanes busy
+// whatever the length of the individual rays (they differ by 50x in this tree; 3 of 32 lanes were busy when every
+// lane was married to one ray, profiles/r1_ncu_extend_*).  Free slots are refilled from the global work counter
+// in batches of >= 32.  Tuning of every constant here: profiles/r1_experiments.md.
 //
 // The per-ray steps are exactly those of traverse.cuh / trace_persistent.cuh (trav_begin, trav_skip,
 // trav_interior arithmetic, leaf_record, pop), executed in the same order for every ray, so results are
@@ -244,8 +245,7 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
 // Compile-time choice of the scheduler used by the kernels (A/B measured in profiles/):
 // 2 = lane refill + vote, 3 = pooled (default).  Measured and removed (profiles/r1_experiments.md, "Schedulers 4 and 5"):
 // scheduler 1 (lane refill + while-while), scheduler 4 (pooled + child-pair node visits: both children fetched and
-// bounds-tested at the parent) and scheduler 5 (k rays owned by every lane, state in conflict-free shared memory).  (Scheduler 1, lane refill + while-while, was measured and removed:
-// profiles/r1_ncu_extend_schedulers.md.)
+// bounds-tested at the parent) and scheduler 5 (k rays owned by every lane, state in conflict-free shared memory).
 #ifndef WRT_TRACE_SCHED
 #define WRT_TRACE_SCHED 3
 #endif
