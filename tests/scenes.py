@@ -222,6 +222,39 @@ def bounce_rays(p, n, mask, salt=7):
     return np.concatenate([o, d], 1).astype(np.float32)
 
 
+# ---- degenerate inputs ------------------------------------------------------------------------------------------
+def edge_scenes():
+    """Degenerate inputs the reference accepts silently: a single primitive, zero-area and duplicated triangles, a sliver,
+    coordinates of very different magnitude, a sphere inside a triangle soup."""
+    base = cornell_box_scene(32, 32)
+    light = base.data[base.matid < 0]
+    def mk(name, tris, extra_kind=None, extra=None):
+        tris = np.asarray(tris, np.float32).reshape(-1, 9)
+        data = tris; kind = np.zeros(len(tris), np.int32); matid = np.ones(len(tris), np.int32)
+        if extra is not None:
+            data = np.concatenate([data, extra]); kind = np.concatenate([kind, extra_kind]); matid = np.concatenate([matid, np.ones(len(extra), np.int32)])
+        data = np.concatenate([data, light]); kind = np.concatenate([kind, np.zeros(len(light), np.int32)])
+        matid = np.concatenate([matid, base.matid[base.matid < 0]])
+        return SceneArrays(name, kind, data.astype(np.float32), matid.astype(np.int32), base.materials, base.lights, base.cam12, 32, 32)
+    one = [[-0.5, 0.2, -0.5, 0.5, 0.2, -0.5, 0.0, 0.2, 0.6]]
+    yield mk("single", one)
+    yield mk("zero_area", one + [[0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1], [0, 0, 0, 1, 1, 1, 2, 2, 2]])
+    yield mk("duplicates", one * 40)
+    yield mk("sliver", one + [[-0.9, 0.5, 0.0, 0.9, 0.5, 0.0, 0.9, 0.5, 1e-6]])
+    rng = np.random.Generator(np.random.PCG64(9))
+    soup = (rng.random((300, 9)) * 1.6 - 0.8).astype(np.float32)
+    yield mk("soup_and_spheres", soup, np.ones(3, np.int32), np.array([[0, 0.3, 0, 0.3, 0, 0, 0, 0, 0], [0.4, 0.1, -0.3, 0.2, 0, 0, 0, 0, 0],
+                                                                         [-0.3, -0.2, 0.4, 0.05, 0, 0, 0, 0, 0]], np.float32))
+    big = soup.copy(); big[:150] *= np.float32(500.0)
+    yield mk("mixed_magnitudes", big)
+    # enough primitives for a tree of > 512 nodes (the GPU's pooled scheduler): small random triangles, a few huge ones
+    c = (rng.random((4000, 1, 3)) * 2 - 1).astype(np.float32)
+    many = (c + (rng.random((4000, 3, 3)).astype(np.float32) - 0.5) * np.float32(0.08)).reshape(-1, 9)
+    many[:6] = (rng.random((6, 9)) * 4 - 2).astype(np.float32)
+    yield mk("many_small_few_huge", many)
+
+
+
 # ---- .scene + OBJ files in the reference's format (for the loader / CLI tests) -----------------------------
 def write_scene_files(sc, out_dir, name="scene"):
     """Writes `sc` (triangles only) as <out_dir>/<name>.scene plus one OBJ per material and one for the light

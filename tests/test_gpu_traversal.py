@@ -200,6 +200,23 @@ def test_c5_class_scene_against_oracle_port_and_exact(wrt):
     assert np.array_equal(p2[0], x2[0]) and np.array_equal(util.bits(p2[1]), util.bits(x2[1]))
 
 
+def test_cuda_edge_scenes(wrt):
+    """Degenerate inputs (single primitive, zero-area / duplicated triangles, sliver, mixed magnitudes, soup + spheres):
+    CUDA EXACT == CUDA PRUNED == oracle port, closest hits and occlusion flags."""
+    for sc in scenes.edge_scenes():
+        port = engines.PortEngine(wrt, sc)
+        with np.errstate(all="ignore"):
+            rays = wrt.make_rays(engines.adversarial_rays(sc, 20000, seed=2))
+        want = port.intersect(rays, full=True)
+        q = scenes.nee_queries(want[2], (want[0] >= 0) & (want[5] > 0), sc.lights)
+        occ = port.occluded(q)
+        for pruned in (False, True):
+            e = engines.CudaEngine(wrt, sc, pruned)
+            got = e.intersect(rays)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(util.bits(got[1]), util.bits(want[1])), (sc.name, pruned)
+            assert np.array_equal(e.occluded(q), occ), (sc.name, pruned)
+
+
 def test_visit_counters_and_stats(wrt):
     sc, z = scenes.load_fixture("torus")
     cuda = engines.CudaEngine(wrt, sc, True); port = engines.PortEngine(wrt, sc)

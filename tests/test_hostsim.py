@@ -165,3 +165,24 @@ def test_hostsim_integrators_match_reference_statistically(wrt, have_ref, kind):
     # PT queues only the shadow rays that can contribute, BDPT skips the BSDF-sampled DI ray when the light
     # sample is occluded: never more rays than the reference, and not fewer than 70 % of them
     assert 0.7 * calls <= rays <= 1.001 * calls
+
+
+def test_edge_scenes_tree_and_traversal(wrt, have_ref):
+    """Builder and traversal on degenerate inputs: our KD-tree equals the reference's (live, where oracle/_ref is built),
+    and EXACT == PRUNED == oracle port on adversarial rays."""
+    for sc in scenes.edge_scenes():
+        hs = util.host_scene(wrt, sc)
+        a = hs.arrays()["tree"]
+        if have_ref:
+            b = util.ref_scene(sc).tree()
+            for k in ("axis", "left", "right", "nref", "refs"):
+                assert np.array_equal(a[k], b[k]), (sc.name, k)
+            inner = b["axis"] >= 0
+            assert np.array_equal(util.bits(a["split"][inner]), util.bits(b["split"][inner])), sc.name
+        port = engines.PortEngine(wrt, sc)
+        with np.errstate(all="ignore"):
+            rays = wrt.make_rays(engines.adversarial_rays(sc, 4000, seed=2))
+        want = port.intersect(rays)
+        for pruned in (False, True):
+            got = engines.HostSimEngine(wrt, sc, pruned).intersect(rays)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(util.bits(got[1]), util.bits(want[1])), (sc.name, pruned)
