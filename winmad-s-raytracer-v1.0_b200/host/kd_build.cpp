@@ -130,7 +130,10 @@ struct Builder {
     {
         if (dep > dep_max || nd->objs.size() <= 1) return false;
         split = 0.f;
+        const bool prof = dep <= 2 && nd->objs.size() > 1000000 && getenv("WRT_KD_PROFILE");
+        const auto tp0 = std::chrono::steady_clock::now();
         axis = find_split(*nd, &split);
+        if (prof) fprintf(stderr, "[kd]   find_split %.2f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
         // No plane with cost < INF-EPS.  The reference indexes box.l[-1] here (undefined behaviour); the only
         // defined reading of the node it leaves is a leaf (axis == -1).
         if (axis < 0) return false;
@@ -157,6 +160,7 @@ struct Builder {
                 to_r[i] = (int)r->objs.size(); r->objs.push_back(nd->objs[i]);
             }
         }
+        if (prof) fprintf(stderr, "[kd]   + classify %.2f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
         const int split_axis = axis;
         const Real split_pos = split;
         auto distribute = [&](int a) {  // :203-276; children inherit the parent's order, never re-sorted
