@@ -1,32 +1,3 @@
-# INTEGRATION — wiring libwrt_b200.so into the reference renderer
-
-`R/` = the reference checkout (`Winmad-s-raytracer-v1.0/`).  The reference has no plugin or FFI
-layer; its seam for this path is two C++ class boundaries (SURVEY.md §8b).  A maintainer adds one
-translation unit (`R/src/surfaceIntegrator/gpuIntegrator.{h,cpp}`, below), two `else if` branches in
-`R/src/main.cpp`, and links `-lwrt_b200`.  Scene parsing, OBJ loading, **KD-tree construction**, camera
-set-up, material/integrator selection and image output stay the reference's own code, unchanged.
-
-## 1. Build
-
-```
-python winmad-s-raytracer-v1.0_b200/build.py           # -> winmad-s-raytracer-v1.0_b200/libwrt_b200.so (sm_100a)
-# in R/Makefile:
-CXXFLAGS += -I /path/to/repo/include
-LDFLAGS  += -L /path/to/repo/winmad-s-raytracer-v1.0_b200 -lwrt_b200 -Wl,-rpath,/path/to/repo/winmad-s-raytracer-v1.0_b200
-```
-
-## 2. The shim (reference-side binding)
-
-The block below is not pseudo-code: it is `oracle/shim_integration/gpuIntegrator.h` byte for byte (a CPU test keeps the two
-identical), `oracle/Makefile` compiles it against the unmodified reference headers and links it with the reference's own
-objects, `oracle/shim_integration/main_gpu.cpp` (the reference's `main.cpp` reduced to this seam plus the three new branches)
-and `libwrt_b200.so` into `oracle/_ref/ToT_gpu`, and `tests/test_gpu_render.py::test_reference_with_shim_renders_on_the_gpu`
-runs `ToT_gpu <scene> <image> -gp | -gr | -gbpt` on a B200 against the reference's own `-p | -r | -bpt` and against `wrt_tot`.
-
-Everything it touches is public in the reference (`Scene::objs`, `KDtreeAccel::root`, `KDtreeAccelNode`,
-`Camera`, `ImageFilm::color`).  `dynamic_cast` needs the reference's own RTTI, which it has (virtual `Geometry`).
-
-```cpp
 // R/src/surfaceIntegrator/gpuIntegrator.h
 #include "pathIntegrator.h"
 #include "bidirPathTracing.h"
@@ -153,57 +124,3 @@ public:
         }
     }
 };
-```
-
-`R/src/main.cpp` gains (next to `-p` / `-bpt`, `main.cpp:40-45,64-69`):
-
-```cpp
-else if (!strcmp(argv[3], "-gp"))   { gpuPath.init(argv[1], para);  gpuPath.render();  gpuPath.outputImage(argv[2]); }
-else if (!strcmp(argv[3], "-gr"))   { gpuWhitted.init(argv[1], para); gpuWhitted.render(); gpuWhitted.outputImage(argv[2]); }
-else if (!strcmp(argv[3], "-gbpt")) { gpuBidir.init(argv[1], para); gpuBidir.render(); gpuBidir.outputImage(argv[2]); }
-```
-
-Level-1 use (any other integrator of the reference that wants batched queries) goes through
-`wrt_trace_closest(dev, rays, n, prim, t)` / `wrt_trace_occluded(dev, p1_dir_p2, n, occluded)`:
-`rays[i]` is the `Ray` object's 8 floats after its constructor; `prim[i]` is the index into `scene.objs`
-(`-1` where `Scene::intersect` returns NULL), so `scene.objs[prim[i]]` is the `Geometry*` the reference would have returned.
-
-## 3. Semantics a caller can rely on
-
-* Same inputs → same primitive ids and bit-identical `t` as `Scene::intersect`; same flags as `Scene::occluded`
-  (tests/test_gpu_traversal.py).  The tree handed over is used as is — never rebuilt or "improved".
-* `wrt_render_pt` returns `ImageFilm::color` after `film->scale(1/spp)`; `wrt_render_bdpt` returns the raw
-  `[x][y]` accumulator (transposed like the reference's) scaled by `film_scale` (default `1/iterations`).
-* Errors: non-zero return + `wrt_last_error()`; the reference's silent failure modes are kept where they are
-  observable behaviour (missing OBJ → no geometry), replaced by an error where the reference would crash
-  (no light in the scene, non-square BDPT film, missing KD-tree).
-* Threading: one calling host thread per `wrt_scene`; one process per GPU (`wrt_set_device(LOCAL_RANK)`);
-  multi-GPU = shard `sample_first/sample_stride` (PT) or `iter_first/iter_stride` (BDPT) and sum the films.
-
-## 4. Python binding (what the tests and bench use)
-
-`import wrt_b200` (alias of `winmad-s-raytracer-v1.0_b200/__init__.py`): ctypes structures mirror `include/wrt.h`
-one to one; `wrt_b200.PathIntegrator().init(scene_file, para).render()` is the Python spelling of the shim above,
-with our own host-side loader/KD builder (`wrt_host_scene_*`) standing in for `Scene::init`.
-`WhittedIntegrator` and `BidirPathTracing` are mirrored the same way (`render()` → `wrt_render_whitted` / `wrt_render_bdpt`).
-
-## 5. Stand-alone command line
-
-`winmad-s-raytracer-v1.0_b200/wrt_tot <scene> <image.ppm|.bmp> -p | -r | -bpt [parameters.para]` is `ToT <scene> <image> <mode>`
-(`R/src/main.cpp:29-97`) for the three integrators on this seam, without the reference in the loop: `.scene` + OBJ files are read by
-`host/scene_io.cpp`, the KD-tree is built by `host/kd_build.cpp` (node-for-node the reference's tree, multi-threaded), the render
-runs on the GPU and the image is written like `ImageFilm::outputImage` (PPM/BMP instead of OpenCV's encoders); `time.txt` is written
-like `main.cpp:93-95`.  `tests/test_gpu_render.py::test_cli_matches_python_api` runs all three modes.
-
-## 6. Environment knobs (all optional)
-
-| variable | effect |
-|---|---|
-| `WRT_POOL_PATHS` | path-pool slots of the PT / Whitted wavefront (default 2^26 ≈ 11.8 GB; clamped to the number of samples) |
-| `WRT_SUBPOOLS` | concurrent sub-pools (streams) of the PT wavefront (default 2) |
-| `WRT_BDPT_BATCH_PATHS` | path slots of a BDPT batch = iterations run side by side × pixels (default 2^24) |
-| `WRT_BDPT_SKIP_GATED=1` | do not trace connection rays whose contribution `controlLength` gates out (the reference traces them) |
-| `WRT_LEAF_SKIP=0`, `WRT_LEAF_SKIP_MIN`, `WRT_LEAF_SKIP_CHUNK` | skip records: off / smallest leaf that gets them (16) / chunk length (6) |
-| `WRT_KD_THREADS` | threads of the host KD build (default: all; 1 = the serial build, same output) |
-| `WRT_BLOCKS_PER_SM`, `WRT_SMEM_CARVEOUT` | experiment knobs of the traversal kernels' launch shape (profiles/r1_experiments.md) |
-| `WRT_B200_LIB` | Python loader only: file name of an A/B build made by `tools/build_variant.sh` |

@@ -257,3 +257,40 @@ def test_cli_matches_python_api(wrt, tmp_path, mode):
     assert img.shape == img2.shape == (64, 64, 3)
     diff = np.abs(img.astype(np.int32) - img2.astype(np.int32))
     assert (diff > 1).mean() < 0.005 and img.mean() > 5
+
+
+@pytest.mark.parametrize("mode", ["p", "r", "bpt"])
+def test_reference_with_shim_renders_on_the_gpu(wrt, tmp_path, mode):
+    """The drop-in itself: oracle/_ref/ToT_gpu = the UNMODIFIED reference (its scene loader, KD builder, camera, film output)
+    + the INTEGRATION.md shim + libwrt_b200.so.  `-g<mode>` (render on the GPU through the shim) against `-<mode>` (the
+    reference's own CPU integrator) on the same scene file: same 8-bit image up to Monte-Carlo noise; and against our own
+    command line `wrt_tot -<mode>` (own loader + own KD builder): the same image up to float-atomics order, which also
+    checks that the reference's tree and ours feed the kernels identically."""
+    import subprocess, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "ToT_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ToT_gpu not built (needs /root/reference at build time)")
+    res = 64
+    sc = scenes.cornell_box_scene(res, res)
+    scene_file = scenes.write_scene_files(sc, str(tmp_path))
+    para = tmp_path / "parameters.para"
+    para.write_text("#MAX_TRACING_DEPTH\n5\n#SAMPLES_PER_PIXEL\n64\n#l\n8\n#h\n4\n#WIDTH\n%d\n#HEIGHT\n%d\n#x\n5\n#y\n400\n" % (res, res))
+    def run(binary, flag, out):
+        r = subprocess.run([binary, scene_file, str(tmp_path / out), flag, str(para)], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        assert "wrt:" not in r.stderr, r.stderr
+        return _read_ppm(str(tmp_path / out)).astype(np.float64)
+    gpu = run(exe, "-g" + mode, "gpu.ppm")
+    cpu = run(exe, "-" + mode, "cpu.ppm")
+    ours = run(os.path.join(os.path.dirname(wrt.LIB_PATH), "wrt_tot"), "-" + mode, "ours.ppm")
+    assert gpu.shape == cpu.shape == ours.shape == (res, res, 3) and gpu.mean() > 5
+    # shim vs our own command line: same renderer, same seed, the reference's tree vs ours
+    assert (np.abs(gpu - ours) > 1).mean() < 0.005
+    # shim vs the reference's CPU integrator: Monte-Carlo estimates of the same image (8-bit, gamma 2.2, clamped)
+    bm = lambda im: im[: res // 8 * 8, : res // 8 * 8].reshape(res // 8, 8, res // 8, 8, 3).mean(axis=(1, 3))
+    if mode == "bpt":      # BidirPathTracing::init fixes iterations = 1: one sample per pixel, only the mean is comparable
+        assert abs(gpu.mean() - cpu.mean()) <= 0.15 * cpu.mean()
+    else:
+        assert abs(gpu.mean() - cpu.mean()) <= 0.03 * cpu.mean()
+        assert np.sqrt(np.mean((bm(gpu) - bm(cpu)) ** 2)) <= 0.05 * cpu.mean()

@@ -166,3 +166,24 @@ def test_film_write(wrt, tmp_path):
     assert raw.startswith(b"P6\n6 4\n255\n")
     px = np.frombuffer(raw[len(b"P6\n6 4\n255\n"):], np.uint8).reshape(4, 6, 3)
     assert tuple(px[1, 2]) == (int(0.5 ** (1 / 2.2) * 255.0), 255, 0)
+
+
+def test_integration_shim_is_the_documented_code_and_links_with_the_reference(wrt, tmp_path):
+    """INTEGRATION.md's reference-side binding is real code: its C++ block is byte for byte oracle/shim_integration/gpuIntegrator.h,
+    which oracle/Makefile compiles against the UNMODIFIED reference headers and links with the reference's own objects and
+    libwrt_b200.so into oracle/_ref/ToT_gpu (the reference's command line + the -gp / -gr / -gbpt branches).  Here: the text
+    matches, and where the binary is built its pure-reference branch (-p) renders a scene file on the CPU."""
+    import re, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.findall(r"```cpp\n(.*?)```", doc, re.S)[0]
+    assert block == open(os.path.join(root, "oracle", "shim_integration", "gpuIntegrator.h")).read()
+    exe = os.path.join(root, "oracle", "_ref", "ToT_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ToT_gpu not built (needs /root/reference at build time)")
+    sc = scenes.cornell_box_scene(32, 32)
+    scene_file = scenes.write_scene_files(sc, str(tmp_path))
+    para = tmp_path / "parameters.para"
+    para.write_text("#MAX_TRACING_DEPTH\n5\n#SAMPLES_PER_PIXEL\n4\n#l\n8\n#h\n4\n#WIDTH\n32\n#HEIGHT\n32\n#x\n5\n#y\n400\n")
+    r = subprocess.run([exe, scene_file, str(tmp_path / "ref.ppm"), "-p", str(para)], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and (tmp_path / "ref.ppm").stat().st_size > 32 * 32 * 3
