@@ -294,3 +294,24 @@ def test_reference_with_shim_renders_on_the_gpu(wrt, tmp_path, mode):
     else:
         assert abs(gpu.mean() - cpu.mean()) <= 0.03 * cpu.mean()
         assert np.sqrt(np.mean((bm(gpu) - bm(cpu)) ** 2)) <= 0.05 * cpu.mean()
+
+
+@pytest.mark.parametrize("which", ["cornell", "torus_mesh"])
+def test_reference_level1_queries_through_the_shim(wrt, tmp_path, which):
+    """Level 1 of the seam inside the reference's own process (ToT_gpu -gcheck): Scene::intersect / Scene::occluded called on
+    the reference's objects, against wrt_trace_closest / wrt_trace_occluded on the scene the shim uploaded (the reference's
+    own loader output and its own KD-tree).  Geometry* identity, bit-identical t, identical occlusion flags."""
+    import subprocess, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "ToT_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ToT_gpu not built (needs /root/reference at build time)")
+    res = 160
+    sc = scenes.cornell_box_scene(res, res) if which == "cornell" else scenes.synthetic_torus_scene(n=64, width=res, height=res)
+    scene_file = scenes.write_scene_files(sc, str(tmp_path))
+    para = tmp_path / "parameters.para"
+    para.write_text("#MAX_TRACING_DEPTH\n5\n#SAMPLES_PER_PIXEL\n1\n#l\n8\n#h\n4\n#WIDTH\n%d\n#HEIGHT\n%d\n#x\n5\n#y\n400\n" % (res, res))
+    r = subprocess.run([exe, scene_file, str(tmp_path / "unused.ppm"), "-gcheck", str(para)], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    print(r.stdout.strip())
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 mismatches" in r.stdout and "level-1 check: %d closest" % 0 not in r.stdout
