@@ -1,10 +1,9 @@
 // Level-1 ray queries behind the C ABI: batch equivalents of Scene::intersect(ray,inter),
 // Scene::intersect(ray), Scene::shadowRayTest and Scene::occluded (R/src/scene/scene.cpp:21-81).
 //
-// Launch shape: persistent warps with lane refill (trace_persistent.cuh).  The grid is (SM count x
-// resident blocks per SM); idle lanes claim new rays from a global counter while busy lanes keep
-// traversing, so long and short rays balance inside a warp and across the machine.  One thread = one
-// ray at a time; the per-thread traversal stack lives in local memory (L1-resident, lane-interleaved).
+// Launch shape: persistent warps, grid = SM count x resident blocks per SM (persistent_grid_for); every warp runs the
+// pooled scheduler of trace_pooled.cuh (64 rays per warp, state in shared memory, stacks in a global scratch area) and
+// pulls work from a global counter until the batch is done.  Trees under 512 nodes use a plain per-thread loop.
 #include <string>
 #include <cstring>
 #include <cstdlib>
