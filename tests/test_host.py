@@ -48,6 +48,7 @@ def test_parallel_kd_build_equals_serial(wrt, monkeypatch):
     sc = scenes.synthetic_torus_scene(n=240, width=64, height=64, n_spheres=2000)
     monkeypatch.setenv("WRT_KD_THREADS", "1")
     a = util.host_scene(wrt, sc).arrays()["tree"]
+    monkeypatch.setenv("WRT_KD_CHUNK_MIN", "50000")      # also split the per-axis event distribution of the top nodes into ranges
     for threads in ("2", "7", "64"):
         monkeypatch.setenv("WRT_KD_THREADS", threads)
         b = util.host_scene(wrt, sc).arrays()["tree"]

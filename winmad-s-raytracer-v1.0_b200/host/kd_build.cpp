@@ -122,6 +122,8 @@ constexpr size_t kParallelAxisMin = 200000;   // events per axis above which the
 struct Builder {
     const std::vector<float>& boxes;  // 6 per prim
     int dep_max;
+    int par_threads;                  // 1 = everything on the calling thread
+    size_t chunk_min_events;          // events per axis above which an axis is distributed in several ranges
 
     // One node of buildTree(), KDtreeAccel.cpp:118-276: termination test, split search, classification and the
     // children's object / event lists.  Returns false when *nd stays a leaf; otherwise consumes nd's lists and
@@ -163,32 +165,56 @@ struct Builder {
         if (prof) fprintf(stderr, "[kd]   + classify %.2f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
         const int split_axis = axis;
         const Real split_pos = split;
-        auto distribute = [&](int a) {  // :203-276; children inherit the parent's order, never re-sorted
-            std::vector<Event>& pe = nd->ev[a];
-            l->ev[a].reserve(l->objs.size() * 2);
-            r->ev[a].reserve(r->objs.size() * 2);
-            for (size_t j = 0; j < pe.size(); j++) {
+        // :203-276; children inherit the parent's order, never re-sorted.  One event range [j0, j1) of axis `a` into the
+        // given child lists (the lists of an axis are filled in event order, so ranges can be processed independently
+        // and concatenated).
+        auto distribute_range = [&](int a, size_t j0, size_t j1, std::vector<Event>& le, std::vector<Event>& re) {
+            const std::vector<Event>& pe = nd->ev[a];
+            for (size_t j = j0; j < j1; j++) {
                 const Event& s = pe[j];
                 Event e;
                 e.type = s.type;
                 const int d = div[s.index];
-                if (d == LeftOnly) { e.pos = s.pos; e.index = to_l[s.index]; l->ev[a].push_back(e); }
-                else if (d == RightOnly) { e.pos = s.pos; e.index = to_r[s.index]; r->ev[a].push_back(e); }
+                if (d == LeftOnly) { e.pos = s.pos; e.index = to_l[s.index]; le.push_back(e); }
+                else if (d == RightOnly) { e.pos = s.pos; e.index = to_r[s.index]; re.push_back(e); }
                 else if (a != split_axis) {
                     e.pos = s.pos;
-                    e.index = to_l[s.index]; l->ev[a].push_back(e);
-                    e.index = to_r[s.index]; r->ev[a].push_back(e);
+                    e.index = to_l[s.index]; le.push_back(e);
+                    e.index = to_r[s.index]; re.push_back(e);
                 } else if (s.type == kEnd) {     // straddler's end: clipped to the plane on the left
-                    e.pos = split_pos; e.index = to_l[s.index]; l->ev[a].push_back(e);
-                    e.pos = s.pos; e.index = to_r[s.index]; r->ev[a].push_back(e);
+                    e.pos = split_pos; e.index = to_l[s.index]; le.push_back(e);
+                    e.pos = s.pos; e.index = to_r[s.index]; re.push_back(e);
                 } else if (s.type == kStart) {   // straddler's start: clipped on the right
-                    e.pos = s.pos; e.index = to_l[s.index]; l->ev[a].push_back(e);
-                    e.pos = split_pos; e.index = to_r[s.index]; r->ev[a].push_back(e);
+                    e.pos = s.pos; e.index = to_l[s.index]; le.push_back(e);
+                    e.pos = split_pos; e.index = to_r[s.index]; re.push_back(e);
+                }
+            }
+        };
+        const size_t n_ev = nd->ev[0].size();
+        const int chunks = (n_ev >= chunk_min_events && par_threads >= 6) ? std::min(par_threads / 3, 8) : 1;
+        auto distribute = [&](int a) {
+            std::vector<Event>& pe = nd->ev[a];
+            l->ev[a].reserve(l->objs.size() * 2);
+            r->ev[a].reserve(r->objs.size() * 2);
+            if (chunks <= 1) distribute_range(a, 0, pe.size(), l->ev[a], r->ev[a]);
+            else {   // large node: the axis in `chunks` ranges on their own threads, concatenated in order
+                std::vector<std::vector<Event>> lp(chunks), rp(chunks);
+                std::vector<std::thread> th;
+                for (int c = 0; c < chunks; c++) {
+                    const size_t j0 = pe.size() * c / chunks, j1 = pe.size() * (c + 1) / chunks;
+                    lp[c].reserve((j1 - j0)); rp[c].reserve((j1 - j0));
+                    th.emplace_back([&, a, c, j0, j1] { distribute_range(a, j0, j1, lp[c], rp[c]); });
+                }
+                for (auto& t : th) t.join();
+                for (int c = 0; c < chunks; c++) {
+                    l->ev[a].insert(l->ev[a].end(), lp[c].begin(), lp[c].end());
+                    r->ev[a].insert(r->ev[a].end(), rp[c].begin(), rp[c].end());
+                    std::vector<Event>().swap(lp[c]); std::vector<Event>().swap(rp[c]);
                 }
             }
             std::vector<Event>().swap(pe);  // parent's list is no longer needed
         };
-        if (nd->ev[0].size() >= kParallelAxisMin) {   // the axes are independent: same lists, three threads
+        if (nd->ev[0].size() >= kParallelAxisMin && par_threads > 1) {   // the axes are independent: same lists, three threads
             std::thread t1(distribute, 1), t2(distribute, 2);
             distribute(0);
             t1.join(); t2.join();
@@ -343,7 +369,9 @@ bool build_kdtree(HostScene& hs, std::string& err)
     }
     for (int a = 0; a < 3; a++) { hs.tree.root_box[a] = root->lo[a]; hs.tree.root_box[3 + a] = root->hi[a]; }
 
-    Builder b = { boxes, hs.tree.dep_max };
+    size_t chunk_min = 4 * kParallelAxisMin;
+    if (const char* e = getenv("WRT_KD_CHUNK_MIN")) chunk_min = (size_t)atoll(e);     // tests lower it to exercise the path
+    Builder b = { boxes, hs.tree.dep_max, threads, chunk_min };
     if (threads > 1) {
         int levels = 1;
         while ((1 << levels) < 2 * threads && levels < 7) levels++;   // ~2 tasks per thread
