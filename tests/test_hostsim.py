@@ -186,3 +186,53 @@ def test_edge_scenes_tree_and_traversal(wrt, have_ref):
         for pruned in (False, True):
             got = engines.HostSimEngine(wrt, sc, pruned).intersect(rays)
             assert np.array_equal(got[0], want[0]) and np.array_equal(util.bits(got[1]), util.bits(want[1])), (sc.name, pruned)
+
+
+# ---- the warp-level schedulers on the CPU (tests/hostsim/warpsim.cpp) ------------------------------------------------
+@pytest.mark.parametrize("sched", [3, 2])
+def test_warpsim_schedulers_match_port(wrt, monkeypatch, sched):
+    """The product's warp-level schedulers themselves — csrc/trace_pooled.cuh (scheduler 3: rings, refill, re-queueing, the
+    global-scratch stacks, early exit of boolean queries) and csrc/trace_persistent.cuh (scheduler 2: lane refill + vote) —
+    compiled for the CPU on an emulation of the warp primitives (one thread per lane, 4 warps) and run on the mixed
+    triangle + sphere golden scene with every leaf chunked into skip records: closest hits (infinite and finite ray.tmax,
+    PRUNED and EXACT) and occlusion flags must equal the oracle port's, and the reference's golden vectors."""
+    from warpsim_py import WarpSim
+    monkeypatch.setenv("WRT_LEAF_SKIP_MIN", "3"); monkeypatch.setenv("WRT_LEAF_SKIP_CHUNK", "2")
+    sc, z = scenes.load_fixture("mixed_torus")
+    hs = util.host_scene(wrt, sc)
+    ws = WarpSim(hs.desc(), hs)
+    port = engines.PortEngine(wrt, sc)
+    n = 2500 if sched == 3 else 1200
+    rays = wrt.make_rays(engines.adversarial_rays(sc, n, seed=4))
+    short = rays.copy(); short[:, 7] = np.random.default_rng(4).uniform(0.05, 4.0, len(rays)).astype(np.float32)
+    for rr in (rays, short):
+        want = port.intersect(rr)
+        for pruned in (True, False):
+            got = ws.trace_closest(rr, pruned, sched)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(util.bits(got[1]), util.bits(want[1])), (sched, pruned)
+    full = port.intersect(rays, full=True)
+    q = scenes.nee_queries(full[2], (full[0] >= 0) & (full[5] > 0), sc.lights)[:n]
+    assert np.array_equal(ws.trace_occluded(q, True, sched), port.occluded(q))
+    # golden primary rays of the fixture (a strided sample): the reference's own answers
+    cam = wrt.Camera.from_ref_array(z["cam45"])
+    prim_rays = wrt.generate_rays(cam, scenes.pixel_centres(512, 512, step=2))
+    sel = np.arange(0, len(prim_rays), 53)[: n]
+    got = ws.trace_closest(prim_rays[sel], True, sched)
+    assert np.array_equal(got[0], z["P_prim"][sel]) and np.array_equal(util.bits(got[1]), util.bits(z["P_t"][sel]))
+
+
+def test_warpsim_nan_interval_and_tiny_batches(wrt):
+    """Pooled scheduler on the CPU: the NaN-interval regression rays (tests above) and batches smaller than a warp / than the
+    refill threshold (1, 5, 33 rays) — exhaustion and partially filled rings."""
+    from warpsim_py import WarpSim
+    sc = scenes.synthetic_torus_scene(n=96, width=64, height=64, n_spheres=2000)
+    hs = util.host_scene(wrt, sc)
+    ws = WarpSim(hs.desc(), hs)
+    port = engines.PortEngine(wrt, sc)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 60000))[13270:13310]
+    want = port.intersect(rays)
+    assert want[0][19] == 965
+    for m in (1, 5, 33, len(rays)):
+        got = ws.trace_closest(rays[:m], True, 3)
+        assert np.array_equal(got[0], want[0][:m]) and np.array_equal(util.bits(got[1]), util.bits(want[1][:m])), m
+    assert len(ws.trace_closest(rays[:0], True, 3)[0]) == 0

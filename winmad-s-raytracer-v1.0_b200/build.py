@@ -79,6 +79,19 @@ def build_hostsim(force=False):
     return out
 
 
+def build_warpsim(force=False):
+    """Test-only library: the warp-level schedulers (csrc/trace_pooled.cuh, trace_persistent.cuh) compiled for the CPU on top
+    of an emulation of CUDA's warp primitives (tests/hostsim/warpsim.cpp).  Never loaded by the product package."""
+    src = os.path.join(ROOT, "tests", "hostsim", "warpsim.cpp")
+    out = os.path.join(ROOT, "tests", "hostsim", "libwrt_warpsim.so")
+    deps = [src, os.path.join(HERE, "csrc/scene_layout.cpp")] + [os.path.join(HERE, h) for h in HEADERS]
+    if force or _newer(out, deps):
+        _run([CXX, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wall", "-Wno-unknown-pragmas",
+              "-Wno-unused-function", "-Wno-unused-variable", "-DWRT_HOSTSIM", "-DWRT_WARPSIM", "-I", os.path.join(HERE, "csrc"),
+              "-o", out, src, os.path.join(HERE, "csrc/scene_layout.cpp"), "-lpthread"])
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose_ptxas="--ptxas" in sys.argv)
     if "--hostsim" in sys.argv:

@@ -46,7 +46,11 @@ __device__ __forceinline__ bool triangle_wins(float p0x, float p0y, float p0z, f
     const float ad = fabsf(denom);
     if (ad > 1e-30f && ad < 1e30f) {
         float rd;
+#if defined(WRT_WARPSIM)
+        rd = 1.0f / denom;      // tests/hostsim/warpsim.cpp (CPU emulation of a warp): any reciprocal inside the margins decides alike
+#else
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(denom));
+#endif
         const float bq = (J * EIHF + K * GFDI + L * DHEG) * rd;
         const float mb = 1e-5f * fabsf(bq) + 2e-8f;
         if (bq < -WRT_EPS - mb || bq > 1.f + mb) return false;                       // certainly rejected on beta
@@ -143,7 +147,7 @@ __device__ __forceinline__ void trace_persistent_vote(const DevSceneView& sc, Sr
                 const int cnt = __popc(need);
                 const int leader = __ffs(need) - 1;
                 unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(counter, (unsigned long long)cnt);
+                if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)cnt);
                 base = __shfl_sync(FULL, base, leader);
                 if (base + (unsigned long long)cnt >= n) exhausted = true;
                 if (!active) {
