@@ -184,7 +184,9 @@ int wrt_trace_shadow(wrt_scene* sc, const wrt_ray* rays, const float* target3, s
 /* bool Scene::occluded(p1, dir, p2)   scene.cpp:71-81: 9 floats per query; dir is normalised by the
  * Ray constructor inside, exactly as the reference does. */
 int wrt_trace_occluded(wrt_scene* sc, const float* p1_dir_p2, size_t n, uint8_t* occluded);
-/* Device-pointer variants (inputs/outputs already resident in HBM; stream = cudaStream_t or NULL). */
+/* Device-pointer variants (inputs/outputs already resident in HBM; stream = cudaStream_t or NULL).  Asynchronous on
+ * `stream`.  Calls on DIFFERENT streams of one scene may overlap: every stream gets its own work counter and traversal
+ * scratch (at most 16 distinct streams per scene); calls on one stream are stream-ordered as usual. */
 int wrt_trace_closest_dev(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_t* d_prim, float* d_t,
                           void* stream);
 int wrt_trace_occluded_dev(wrt_scene* sc, const float* d_p1_dir_p2, size_t n, uint8_t* d_occluded,
@@ -198,7 +200,9 @@ int wrt_trace_count_visits(wrt_scene* sc, const wrt_ray* rays, size_t n);
  * (surfaceIntegrator.cpp:14-46, pathIntegrator.cpp:29-148).  film: H x W x 3 floats, film[i][j] as
  * ImageFilm::color[i][j] after film->scale(1/spp). */
 int wrt_render_pt(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* film_hw3);
-/* Device film (accumulated into: caller zeroes it); no host copy; asynchronous on `stream`. */
+/* Device film (accumulated into: caller zeroes it); no host copy.  The work is ordered after everything queued on
+ * `stream` so far; the call itself returns when the render has finished (it is NOT asynchronous).
+ * All wrt_render_* calls on one wrt_scene must come from one host thread at a time. */
 int wrt_render_pt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film_hw3,
                       void* stream);
 /* WhittedIntegrator: SurfaceIntegrator::render + WhittedIntegrator::raytracing (surfaceIntegrator.cpp:14-46,

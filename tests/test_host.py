@@ -188,3 +188,63 @@ def test_integration_shim_is_the_documented_code_and_links_with_the_reference(wr
     para.write_text("#MAX_TRACING_DEPTH\n5\n#SAMPLES_PER_PIXEL\n4\n#l\n8\n#h\n4\n#WIDTH\n32\n#HEIGHT\n32\n#x\n5\n#y\n400\n")
     r = subprocess.run([exe, scene_file, str(tmp_path / "ref.ppm"), "-p", str(para)], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and (tmp_path / "ref.ppm").stat().st_size > 32 * 32 * 3
+
+
+def test_cache_rejects_damaged_files(wrt, tmp_path):
+    """a truncated / corrupt / stale-format cache must fail with an error code, not terminate the process
+    (absurd element counts are bounded by the file size before any allocation; arrays are cross-checked; the geometry
+    fingerprint is re-computed)."""
+    sc = scenes.small_mixed_scene()
+    hs = util.host_scene(wrt, sc)
+    p = str(tmp_path / "s.wrtscene")
+    hs.save(p)
+    raw = open(p, "rb").read()
+    cases = {
+        "truncated": raw[: len(raw) // 2],
+        "huge_count": raw[:24] + (2 ** 62).to_bytes(8, "little") + raw[32:],     # first array claims 2^62 elements
+        "old_magic": b"WRTSCN01" + raw[8:],
+        "flipped_vertex": raw[:200] + bytes([raw[200] ^ 0x40]) + raw[201:],       # inside prim_data: fingerprint mismatch
+        "empty": b"",
+    }
+    for name, blob in cases.items():
+        q = str(tmp_path / (name + ".wrtscene"))
+        open(q, "wb").write(blob)
+        with pytest.raises(wrt.WrtError):
+            wrt.HostScene.load_cache(q)
+    assert wrt.HostScene.load_cache(p).arrays()["prim_kind"].shape == hs.arrays()["prim_kind"].shape
+
+
+def test_layout_rejects_what_the_kernels_cannot_index(wrt):
+    """material / light ids past their tables and trees deeper than the traversal stack are refused when the
+    layout is built (the kernels index materials[matid], lights[-matid-1] and a 32-entry stack without checks)."""
+    from hostsim_py import HostSim
+    sc = scenes.small_mixed_scene()
+    hs = util.host_scene(wrt, sc)
+    a = hs.arrays()
+    t = a["tree"]
+
+    def build(matid=None, tree=None):
+        d, keep = wrt.desc_from_arrays(a["prim_kind"], a["prim_data"], a["prim_matid"] if matid is None else matid,
+                                       a["materials"], a["lights"], tree or t)
+        return HostSim(d, keep)
+
+    build()                                                   # the untouched scene is fine
+    bad = a["prim_matid"].copy(); bad[0] = len(a["materials"])
+    with pytest.raises(RuntimeError, match="material id"):
+        build(matid=bad)
+    bad = a["prim_matid"].copy(); bad[0] = -(len(a["lights"]) + 1)
+    with pytest.raises(RuntimeError, match="light"):
+        build(matid=bad)
+    # a degenerate chain of 40 interior nodes above the real root
+    n0 = len(t["axis"]); extra = 40
+    chain = dict(t)
+    axis = np.concatenate([np.zeros(extra, np.int32), t["axis"], np.full(extra, -1, np.int32)])
+    split = np.concatenate([np.full(extra, -1e6, np.float32), t["split"], np.zeros(extra, np.float32)])
+    # chain node i: left = empty leaf (extra + n0 + i), right = next chain node (or the old root)
+    left = np.concatenate([extra + n0 + np.arange(extra, dtype=np.int32), np.where(t["left"] >= 0, t["left"] + extra, -1), np.full(extra, -1, np.int32)])
+    right = np.concatenate([np.arange(1, extra + 1, dtype=np.int32), np.where(t["right"] >= 0, t["right"] + extra, -1), np.full(extra, -1, np.int32)])
+    first = np.concatenate([np.full(extra, -1, np.int32), t["first_ref"], np.zeros(extra, np.int32)])
+    nref = np.concatenate([np.zeros(extra, np.int32), t["nref"], np.zeros(extra, np.int32)])
+    chain.update(axis=axis, split=split, left=left.astype(np.int32), right=right.astype(np.int32), first_ref=first, nref=nref)
+    with pytest.raises(RuntimeError, match="too deep"):
+        build(tree=chain)

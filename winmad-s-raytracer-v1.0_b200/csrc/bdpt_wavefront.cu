@@ -225,6 +225,21 @@ void bdpt_destroy(wrt_wavefront* wf)
     wf->bdpt = nullptr;
 }
 
+static int bdpt_alloc(BdptBuffers* B, unsigned n_paths, int maxv)
+{
+    const size_t conn_cap = (size_t)n_paths * (size_t)(maxv + 1);
+    WRT_CUDA(cudaMalloc((void**)&B->dvc, (size_t)n_paths * sizeof(float)));
+    WRT_CUDA(cudaMalloc((void**)&B->verts, (size_t)n_paths * maxv * 4 * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->nverts, (size_t)n_paths * sizeof(int)));
+    WRT_CUDA(cudaMalloc((void**)&B->conn.a, conn_cap * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->conn.b, conn_cap * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->conn.c, conn_cap * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->conn.pixel, conn_cap * sizeof(uint32_t)));
+    WRT_CUDA(cudaMalloc((void**)&B->di, (size_t)n_paths * 6 * sizeof(float4)));
+    return WRT_OK;
+}
+
+// The buffers are published in wf->bdpt (with their sizes) only after every allocation has succeeded.
 static int bdpt_buffers(wrt_wavefront* wf, unsigned n_paths, int maxv, BdptBuffers** out)
 {
     BdptBuffers* B = (BdptBuffers*)wf->bdpt;
@@ -235,18 +250,16 @@ static int bdpt_buffers(wrt_wavefront* wf, unsigned n_paths, int maxv, BdptBuffe
     bdpt_destroy(wf);
     B = new BdptBuffers();
     memset(B, 0, sizeof *B);
-    wf->bdpt = B;
+    const int rc = bdpt_alloc(B, n_paths, maxv);
+    if (rc != WRT_OK) {
+        wf->bdpt = B; bdpt_destroy(wf);      // frees the partial allocation, leaves wf->bdpt == nullptr
+        cudaGetLastError();
+        return rc;
+    }
     B->n_paths = n_paths; B->maxv = maxv;
     B->conn_cap = (size_t)n_paths * (size_t)(maxv + 1);
     B->di_cap = n_paths;
-    WRT_CUDA(cudaMalloc((void**)&B->dvc, (size_t)n_paths * sizeof(float)));
-    WRT_CUDA(cudaMalloc((void**)&B->verts, (size_t)n_paths * maxv * 4 * sizeof(float4)));
-    WRT_CUDA(cudaMalloc((void**)&B->nverts, (size_t)n_paths * sizeof(int)));
-    WRT_CUDA(cudaMalloc((void**)&B->conn.a, B->conn_cap * sizeof(float4)));
-    WRT_CUDA(cudaMalloc((void**)&B->conn.b, B->conn_cap * sizeof(float4)));
-    WRT_CUDA(cudaMalloc((void**)&B->conn.c, B->conn_cap * sizeof(float4)));
-    WRT_CUDA(cudaMalloc((void**)&B->conn.pixel, B->conn_cap * sizeof(uint32_t)));
-    WRT_CUDA(cudaMalloc((void**)&B->di, B->di_cap * 6 * sizeof(float4)));
+    wf->bdpt = B;
     *out = B;
     return WRT_OK;
 }
@@ -306,18 +319,18 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
     const bool counting = sc->counting != 0;
     const bool count_pruned = sc->counting == 2;
 
-    static int g_li = persistent_grid_for((const void*)k_bdpt_light_init, kBlock);
-    static int g_ci = persistent_grid_for((const void*)k_bdpt_camera_init, kBlock);
-    static int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
-    static int g_ext_e = persistent_grid_for((const void*)k_pt_extend<false>, kBlock);
-    static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count<false>, kBlock);
-    static int g_ls = persistent_grid_for((const void*)k_bdpt_light_shade, kBlock);
-    static int g_cs = persistent_grid_for((const void*)k_bdpt_camera_shade, kBlock);
-    static int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
-    static int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
-    static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count<false>, kBlock);
-    static int g_di_p = persistent_grid_for((const void*)k_bdpt_di<true>, kBlock);
-    static int g_di_e = persistent_grid_for((const void*)k_bdpt_di<false>, kBlock);
+    const int g_li = persistent_grid_for((const void*)k_bdpt_light_init, kBlock);
+    const int g_ci = persistent_grid_for((const void*)k_bdpt_camera_init, kBlock);
+    const int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
+    const int g_ext_e = persistent_grid_for((const void*)k_pt_extend<false>, kBlock);
+    const int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count<false>, kBlock);
+    const int g_ls = persistent_grid_for((const void*)k_bdpt_light_shade, kBlock);
+    const int g_cs = persistent_grid_for((const void*)k_bdpt_camera_shade, kBlock);
+    const int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
+    const int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
+    const int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count<false>, kBlock);
+    const int g_di_p = persistent_grid_for((const void*)k_bdpt_di<true>, kBlock);
+    const int g_di_e = persistent_grid_for((const void*)k_bdpt_di<false>, kBlock);
 
     rc = wavefront_events(wf, 4 * 64);
     if (rc) return rc;

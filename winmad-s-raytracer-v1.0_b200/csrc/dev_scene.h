@@ -9,7 +9,7 @@ namespace wrt {
 
 #define WRT_EPS 1e-3f
 #define WRT_INF 1e7f
-#define WRT_STACK_DEPTH 40      /* reference: depMax + 5 = (int)(1.2 ln N + 2) + 5; 29 at N = 1e8 */
+#define WRT_STACK_DEPTH 32      /* ONE bound for every scheduler; deeper trees are refused by build_layout (reference: depMax + 5 <= 29 at N = 1e8) */
 #define WRT_LEAF_TAG 3u
 #define WRT_REC_SKIP 2          /* leaf record kind: conservative box of the next n records (kinds 0 / 1: triangle / sphere) */
 
@@ -62,6 +62,12 @@ struct DevSceneView {  // passed to kernels by value
 }  // namespace wrt
 
 #ifdef __CUDACC__
+#define WRT_MAX_TRACE_STREAMS 16
+struct wrt_trace_ctx {               // per caller stream: work counter + traversal-stack scratch (trace_kernels.cu)
+    cudaStream_t stream;
+    unsigned long long* counter;
+    void* scratch; size_t scratch_bytes;
+};
 struct wrt_scene {
     wrt::DevSceneView view;
     int device;
@@ -75,6 +81,7 @@ struct wrt_scene {
     void* d_scratch_out; size_t scratch_out_bytes;
     unsigned long long* d_counters;  // small device counter block
     void* d_trav_scratch; size_t trav_scratch_bytes;   // pooled scheduler's traversal stacks (API calls on `stream`)
+    wrt_trace_ctx trace_ctx[WRT_MAX_TRACE_STREAMS]; int n_trace_ctx;   // device-pointer entry points: one per caller stream
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev_fork;
     struct wrt_wavefront* wf;        // lazily created integrator state (sub-pool 0; owns the film and BDPT buffers)

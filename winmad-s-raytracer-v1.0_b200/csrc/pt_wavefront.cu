@@ -199,15 +199,10 @@ __global__ void k_film_resolve(const float* __restrict__ film, size_t n, float s
 // ---- wavefront state -------------------------------------------------------------------------------
 static void wavefront_free(wrt_wavefront* wf);
 
-int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** out)
+// Allocation failures leave NO half-built object behind: the slot is published (and its capacity becomes visible to the
+// `capacity >= requested` check of the next call) only after every allocation has succeeded.
+static int wavefront_alloc(wrt_wavefront* wf, int capacity)
 {
-    wrt_wavefront** where = slot == 0 ? &sc->wf : &sc->wf_extra[slot - 1];
-    if (*where && (*where)->capacity >= capacity) { *out = *where; return WRT_OK; }
-    if (*where) { wavefront_free(*where); *where = nullptr; }
-    wrt_wavefront* wf = new wrt_wavefront();
-    memset(wf, 0, sizeof *wf);
-    wf->capacity = capacity;
-    *where = wf;
     const size_t P = (size_t)capacity;
     WRT_CUDA(cudaMalloc((void**)&wf->pool.ray, P * sizeof(wrt_ray)));
     WRT_CUDA(cudaMalloc((void**)&wf->pool.weight_pdf, P * sizeof(float4)));
@@ -225,6 +220,24 @@ int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** ou
     WRT_CUDA(cudaStreamCreateWithFlags(&wf->stream, cudaStreamNonBlocking));
     { int rc = ensure_trav_scratch(&wf->trav_scratch, &wf->trav_scratch_bytes); if (rc) return rc; }
     WRT_CUDA(cudaEventCreateWithFlags(&wf->join_ev, cudaEventDisableTiming));
+    return WRT_OK;
+}
+
+int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** out)
+{
+    wrt_wavefront** where = slot == 0 ? &sc->wf : &sc->wf_extra[slot - 1];
+    if (*where && (*where)->capacity >= capacity) { *out = *where; return WRT_OK; }
+    if (*where) { wavefront_free(*where); *where = nullptr; }
+    wrt_wavefront* wf = new wrt_wavefront();
+    memset(wf, 0, sizeof *wf);
+    const int rc = wavefront_alloc(wf, capacity);
+    if (rc != WRT_OK) {
+        wavefront_free(wf);          // frees whatever was allocated; the slot stays empty
+        cudaGetLastError();          // an out-of-memory cudaMalloc is not sticky: clear it for the next call
+        return rc;
+    }
+    wf->capacity = capacity;
+    *where = wf;
     *out = wf;
     return WRT_OK;
 }
@@ -279,7 +292,7 @@ static void wavefront_free(wrt_wavefront* wf)
     cudaFree(wf->pool.hit_prim); cudaFree(wf->pool.hit_t);
     cudaFree(wf->queue[0]); cudaFree(wf->queue[1]);
     cudaFree(wf->shadow.a); cudaFree(wf->shadow.b); cudaFree(wf->shadow.c); cudaFree(wf->shadow.pixel);
-    cudaFree(wf->counters); cudaFreeHost(wf->h_counters); cudaFree(wf->film); cudaFree(wf->trav_scratch); cudaFree(wf->whitted);
+    cudaFree(wf->counters); if (wf->h_counters) cudaFreeHost(wf->h_counters); cudaFree(wf->film); cudaFree(wf->trav_scratch); cudaFree(wf->whitted);
     for (int i = 0; i < wf->n_ev; i++) cudaEventDestroy(wf->ev[i]);
     delete[] wf->ev;
     if (wf->stream) cudaStreamDestroy(wf->stream);
@@ -378,6 +391,9 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     PtParams P;
     int rc = pt_fill_params(p, P);
     if (rc) return rc;
+    if (whitted && P.max_depth > 63) {   // the per-slot pending list holds one parked child per level
+        set_error("wrt_render_whitted: max_depth > 63 is not supported (the ray tree's pending list has 64 levels)"); return WRT_ERR_INVALID;
+    }
     DevCamera dc; fill_camera(cam, dc);
     PtPlan plan; pt_plan(P, plan, whitted);
     SubState sub[8];
@@ -394,15 +410,15 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     const bool counting = sc->counting != 0;
     const bool count_pruned = sc->counting == 2;
 
-    static int g_init = persistent_grid_for((const void*)k_pt_init, kBlock);
-    static int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
-    static int g_ext_e = persistent_grid_for((const void*)k_pt_extend<false>, kBlock);
-    static int g_shade = persistent_grid_for((const void*)k_pt_shade, kBlock);
-    static int g_wshade = persistent_grid_for((const void*)k_wh_shade, kBlock);
-    static int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
-    static int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
-    static int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count<false>, kBlock);
-    static int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count<false>, kBlock);
+    const int g_init = persistent_grid_for((const void*)k_pt_init, kBlock);
+    const int g_ext_p = persistent_grid_for((const void*)k_pt_extend<true>, kBlock);
+    const int g_ext_e = persistent_grid_for((const void*)k_pt_extend<false>, kBlock);
+    const int g_shade = persistent_grid_for((const void*)k_pt_shade, kBlock);
+    const int g_wshade = persistent_grid_for((const void*)k_wh_shade, kBlock);
+    const int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
+    const int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
+    const int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count<false>, kBlock);
+    const int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count<false>, kBlock);
 
     // initial fill: sub-pool j starts with samples [first, first + n0_j)
     unsigned long long first = 0;

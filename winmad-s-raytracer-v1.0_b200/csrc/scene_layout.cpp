@@ -150,10 +150,13 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
     std::vector<int32_t> order;            // new index -> old index
     std::vector<int32_t> pair_of(nn, -1);  // old interior index -> new index of its left child
     std::vector<char> seen(nn, 0);
+    std::vector<int32_t> above(nn, 0);     // old index -> interior nodes on the way from the root (= stack entries a ray can hold there)
+    int max_above = 0;
     order.reserve(nn);
     order.push_back(0); seen[0] = 1;
     for (size_t head = 0; head < order.size(); head++) {
         const int o = order[head];
+        max_above = std::max(max_above, (int)above[o]);
         if (T.axis[o] == -1) continue;
         if (T.axis[o] < 0 || T.axis[o] > 2) { set_error("node axis out of range"); return false; }
         const int l = T.left[o], r = T.right[o];
@@ -162,10 +165,19 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
             return false;
         }
         seen[l] = seen[r] = 1;
+        above[l] = above[r] = above[o] + 1;
         pair_of[o] = (int32_t)order.size();
         order.push_back(l); order.push_back(r);
     }
     const int n_live = (int)order.size();
+    // A ray holds at most one pending far child per interior node above it.  The traversal stacks (per-thread and the
+    // pooled scheduler's scratch) have WRT_STACK_DEPTH entries; a deeper tree is refused here instead of silently
+    // dropping far children in the kernels (the reference's own bound is depMax + 5 <= 29 for 1e8 primitives).
+    if (max_above > WRT_STACK_DEPTH) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "kd-tree too deep: %d interior levels, the traversal stack holds %d", max_above, WRT_STACK_DEPTH);
+        set_error(buf); return false;
+    }
 
     // ---- leaf records --------------------------------------------------------------------------
     const SkipCfg skips = skip_config();
@@ -189,6 +201,10 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
         if (d->prim_kind[i] != WRT_PRIM_TRIANGLE && d->prim_kind[i] != WRT_PRIM_SPHERE) {
             set_error("unknown primitive kind"); return false;
         }
+        // the shaders index materials[matid] / lights[-matid-1] directly (the reference reads out of bounds here)
+        const int m = d->prim_matid[i];
+        if (m > 0 && m >= d->n_materials) { set_error("primitive material id past the material table"); return false; }
+        if (m < 0 && (-(int64_t)m - 1) >= d->n_lights) { set_error("emitter primitive refers to a light past the light table"); return false; }
         float* b = &pboxes[6 * (size_t)i];
         if (d->prim_kind[i] == WRT_PRIM_SPHERE) {  // Sphere::setBox + AABB::extend
             for (int a = 0; a < 3; a++) { b[a] = pd[a] - pd[3]; b[3 + a] = pd[a] + pd[3]; }

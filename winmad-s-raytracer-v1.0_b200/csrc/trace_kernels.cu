@@ -7,6 +7,9 @@
 #include <string>
 #include <cstring>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "trace_pooled.cuh"
 #include "warp_utils.cuh"
 
@@ -174,7 +177,9 @@ int ensure_trav_scratch(void** ptr, size_t* bytes)
     return WRT_OK;
 }
 
-int persistent_grid_for(const void* kernel, int block)
+// Grid of a persistent kernel on the CURRENT device: SM count x resident blocks per SM.  Cached per (device, kernel) —
+// a process may drive several devices (wrt_init), so the value must not be a function-local static.
+static int persistent_grid_uncached(const void* kernel, int block)
 {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
@@ -195,18 +200,57 @@ int persistent_grid_for(const void* kernel, int block)
     return sms * per_sm;
 }
 
+int persistent_grid_for(const void* kernel, int block)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(dev, kernel);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const int g = persistent_grid_uncached(kernel, block);
+    cache[key] = g;
+    return g;
+}
+
+// Work counter + traversal-stack scratch of one caller stream.  The device-pointer entry points take a stream; two calls on
+// different streams of one scene must not share the counter (one zeroes it while the other fetches work) nor the [depth][slot]
+// stack scratch, so every stream seen gets its own pair (created on first use, kept for the life of the scene).
+int trace_ctx_for(wrt_scene* sc, cudaStream_t st, unsigned long long** counter, float4** scratch)
+{
+    for (int i = 0; i < sc->n_trace_ctx; i++)
+        if (sc->trace_ctx[i].stream == st) { *counter = sc->trace_ctx[i].counter; *scratch = (float4*)sc->trace_ctx[i].scratch; return WRT_OK; }
+    if (sc->n_trace_ctx >= WRT_MAX_TRACE_STREAMS) {
+        set_error("wrt_trace_*_dev: more than 16 distinct streams used on one scene"); return WRT_ERR_INVALID;
+    }
+    wrt_trace_ctx c; memset(&c, 0, sizeof c);
+    c.stream = st;
+    cudaError_t e = cudaMalloc((void**)&c.counter, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(c.counter, 0, 16 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { cudaFree(c.counter); cudaGetLastError(); return cuda_fail(e, "trace context"); }
+    const int rc = ensure_trav_scratch(&c.scratch, &c.scratch_bytes);
+    if (rc) { cudaFree(c.counter); cudaGetLastError(); return rc; }
+    sc->trace_ctx[sc->n_trace_ctx++] = c;
+    *counter = c.counter; *scratch = (float4*)c.scratch;
+    return WRT_OK;
+}
+
 // d_counters layout: [0] work counter, [8..11] visit sums
 static int launch_closest(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_t* d_prim, float* d_t,
                           float* d_p, float* d_n, int32_t* d_inside, int32_t* d_matid, cudaStream_t st)
 {
     if (n == 0) return WRT_OK;
-    WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
+    unsigned long long* ctr; float4* scr;
+    { int rc = trace_ctx_for(sc, st, &ctr, &scr); if (rc) return rc; }
+    WRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
     if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
-        static int grid = persistent_grid_for((const void*)k_trace_closest<true>, kTraceBlock);
-        k_trace_closest<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, sc->d_counters, (float4*)sc->d_trav_scratch);
+        const int grid = persistent_grid_for((const void*)k_trace_closest<true>, kTraceBlock);
+        k_trace_closest<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, ctr, scr);
     } else {
-        static int grid = persistent_grid_for((const void*)k_trace_closest<false>, kTraceBlock);
-        k_trace_closest<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, sc->d_counters, (float4*)sc->d_trav_scratch);
+        const int grid = persistent_grid_for((const void*)k_trace_closest<false>, kTraceBlock);
+        k_trace_closest<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_rays, n, d_prim, d_t, d_p, d_n, d_inside, d_matid, ctr, scr);
     }
     WRT_CUDA(cudaGetLastError());
     sc->stats.closest_rays += n;
@@ -217,13 +261,15 @@ static int launch_closest(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_
 static int launch_occluded(wrt_scene* sc, const float* d_q9, size_t n, uint8_t* d_occ, cudaStream_t st)
 {
     if (n == 0) return WRT_OK;
-    WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
+    unsigned long long* ctr; float4* scr;
+    { int rc = trace_ctx_for(sc, st, &ctr, &scr); if (rc) return rc; }
+    WRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
     if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
-        static int grid = persistent_grid_for((const void*)k_trace_occluded<true>, kTraceBlock);
-        k_trace_occluded<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, sc->d_counters, (float4*)sc->d_trav_scratch);
+        const int grid = persistent_grid_for((const void*)k_trace_occluded<true>, kTraceBlock);
+        k_trace_occluded<true><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, ctr, scr);
     } else {
-        static int grid = persistent_grid_for((const void*)k_trace_occluded<false>, kTraceBlock);
-        k_trace_occluded<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, sc->d_counters, (float4*)sc->d_trav_scratch);
+        const int grid = persistent_grid_for((const void*)k_trace_occluded<false>, kTraceBlock);
+        k_trace_occluded<false><<<grid, kTraceBlock, 0, st>>>(sc->view, d_q9, n, d_occ, ctr, scr);
     }
     WRT_CUDA(cudaGetLastError());
     sc->stats.shadow_rays += n;
@@ -290,10 +336,10 @@ int wrt_trace_any(wrt_scene* sc, const wrt_ray* rays, size_t n, uint8_t* hit)
     WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
     WRT_CUDA(cudaEventRecord(sc->ev0, st));
     if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
-        static int grid = persistent_grid_for((const void*)k_trace_any<true>, kTraceBlock);
+        const int grid = persistent_grid_for((const void*)k_trace_any<true>, kTraceBlock);
         k_trace_any<true><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, sc->d_counters, (float4*)sc->d_trav_scratch);
     } else {
-        static int grid = persistent_grid_for((const void*)k_trace_any<false>, kTraceBlock);
+        const int grid = persistent_grid_for((const void*)k_trace_any<false>, kTraceBlock);
         k_trace_any<false><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, (uint8_t*)sc->d_scratch_out, sc->d_counters, (float4*)sc->d_trav_scratch);
     }
     WRT_CUDA(cudaGetLastError());
@@ -320,10 +366,10 @@ int wrt_trace_shadow(wrt_scene* sc, const wrt_ray* rays, const float* target3, s
     WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long), st));
     WRT_CUDA(cudaEventRecord(sc->ev0, st));
     if (sc->traversal_mode == WRT_TRAVERSE_PRUNED) {
-        static int grid = persistent_grid_for((const void*)k_trace_shadow<true>, kTraceBlock);
+        const int grid = persistent_grid_for((const void*)k_trace_shadow<true>, kTraceBlock);
         k_trace_shadow<true><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)in, d_target, n, (float*)sc->d_scratch_out, sc->d_counters, (float4*)sc->d_trav_scratch);
     } else {
-        static int grid = persistent_grid_for((const void*)k_trace_shadow<false>, kTraceBlock);
+        const int grid = persistent_grid_for((const void*)k_trace_shadow<false>, kTraceBlock);
         k_trace_shadow<false><<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)in, d_target, n, (float*)sc->d_scratch_out, sc->d_counters, (float4*)sc->d_trav_scratch);
     }
     WRT_CUDA(cudaGetLastError());
@@ -381,7 +427,7 @@ int wrt_trace_count_visits(wrt_scene* sc, const wrt_ray* rays, size_t n)
     cudaStream_t st = sc->stream;
     WRT_CUDA(cudaMemcpyAsync(sc->d_scratch_in, rays, n * sizeof(wrt_ray), cudaMemcpyHostToDevice, st));
     WRT_CUDA(cudaMemsetAsync(sc->d_counters, 0, 16 * sizeof(unsigned long long), st));
-    static int grid = persistent_grid_for((const void*)k_count_visits, kTraceBlock);
+    const int grid = persistent_grid_for((const void*)k_count_visits, kTraceBlock);
     k_count_visits<<<grid, kTraceBlock, 0, st>>>(sc->view, (const wrt_ray*)sc->d_scratch_in, n, sc->d_counters, sc->d_counters + 8);
     WRT_CUDA(cudaGetLastError());
     sc->stats.kernel_launches += 1;

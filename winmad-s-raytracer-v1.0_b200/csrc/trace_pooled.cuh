@@ -21,7 +21,7 @@ namespace wrt {
 #define WRT_POOL_RAYS 64
 #endif
 constexpr int kPoolRays = WRT_POOL_RAYS;   // rays per warp (power of two, <= 256)
-constexpr int kPoolStack = 32;         // stack entries per ray (reference: depMax + 5, <= 29 for 1e8 primitives)
+constexpr int kPoolStack = WRT_STACK_DEPTH;   // stack entries per ray; build_layout refuses trees that could overflow it
 #ifndef WRT_POOL_NODE_STEPS
 #define WRT_POOL_NODE_STEPS 6
 #endif

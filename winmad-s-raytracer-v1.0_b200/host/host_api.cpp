@@ -1,6 +1,7 @@
 // C-ABI entry points that run on the host only (include/wrt.h, "host side" block).
 #include <cstring>
 #include <new>
+#include <exception>
 #include "host_scene.h"
 
 struct wrt_host_scene {
@@ -14,6 +15,11 @@ void set_error(const std::string& s) { g_last_error = s; }
 
 using wrt::set_error;
 
+// No C++ exception may cross the C boundary (a corrupt file or an absurd size must not terminate the caller).
+#define WRT_GUARD_BEGIN try {
+#define WRT_GUARD_END(h_to_free) } catch (const std::bad_alloc&) { delete (h_to_free); set_error("out of memory"); return WRT_ERR_NOMEM; } \
+    catch (const std::exception& e__) { delete (h_to_free); set_error(std::string("internal error: ") + e__.what()); return WRT_ERR_INVALID; }
+
 extern "C" {
 
 const char* wrt_version(void) { return "wrt-b200 0.1 (sm_100a)"; }
@@ -24,8 +30,10 @@ int wrt_host_scene_load(const char* scene_file, wrt_host_scene** out)
     if (!scene_file || !out) { set_error("wrt_host_scene_load: null argument"); return WRT_ERR_INVALID; }
     wrt_host_scene* h = new (std::nothrow) wrt_host_scene();
     if (!h) { set_error("out of memory"); return WRT_ERR_NOMEM; }
+    WRT_GUARD_BEGIN
     std::string err;
     if (!wrt::load_scene_file(scene_file, h->hs, err)) { set_error(err); delete h; return WRT_ERR_IO; }
+    WRT_GUARD_END(h)
     *out = h;
     return WRT_OK;
 }
@@ -49,6 +57,7 @@ int wrt_host_scene_from_arrays(int32_t n_materials, const float* materials11, in
     wrt_host_scene* h = new (std::nothrow) wrt_host_scene();
     if (!h) { set_error("out of memory"); return WRT_ERR_NOMEM; }
     wrt::HostScene& hs = h->hs;
+    WRT_GUARD_BEGIN
     hs.materials.assign(materials11, materials11 + (size_t)11 * n_materials);
     hs.prim_kind.assign(prim_kind, prim_kind + n_prims);
     hs.prim_data.assign(prim_data9, prim_data9 + (size_t)9 * n_prims);
@@ -59,6 +68,7 @@ int wrt_host_scene_from_arrays(int32_t n_materials, const float* materials11, in
         wrt::camera_setup(cam12, cam12 + 3, cam12 + 6, cam12[9], cam12[10], cam12[11], &hs.camera);
         hs.has_camera = true;
     }
+    WRT_GUARD_END(h)
     *out = h;
     return WRT_OK;
 }
@@ -66,8 +76,10 @@ int wrt_host_scene_from_arrays(int32_t n_materials, const float* materials11, in
 int wrt_host_scene_build_kdtree(wrt_host_scene* h)
 {
     if (!h) { set_error("null scene"); return WRT_ERR_INVALID; }
+    WRT_GUARD_BEGIN
     std::string err;
     if (!wrt::build_kdtree(h->hs, err)) { set_error(err); return WRT_ERR_INVALID; }
+    WRT_GUARD_END((wrt_host_scene*)nullptr)
     return WRT_OK;
 }
 
@@ -122,8 +134,10 @@ int wrt_host_scene_load_cache(const char* path, wrt_host_scene** out)
     if (!path || !out) { set_error("null argument"); return WRT_ERR_INVALID; }
     wrt_host_scene* h = new (std::nothrow) wrt_host_scene();
     if (!h) { set_error("out of memory"); return WRT_ERR_NOMEM; }
+    WRT_GUARD_BEGIN
     std::string err;
     if (!wrt::load_cache(path, h->hs, err)) { set_error(err); delete h; return WRT_ERR_IO; }
+    WRT_GUARD_END(h)
     *out = h;
     return WRT_OK;
 }

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
+#include <climits>
 #include <fstream>
 #include <sstream>
 #include "host_scene.h"
@@ -480,18 +482,42 @@ bool film_write(const char* path, const float* film, int w, int h, float scale, 
 // flattened-scene cache
 // ------------------------------------------------------------------------------------------------
 namespace {
-const char kMagic[8] = { 'W', 'R', 'T', 'S', 'C', 'N', '0', '1' };
+// Format 02: magic, then {u32 layout version, u32 sizeof(wrt_camera), u64 content fingerprint}, then the arrays.
+// The fingerprint (FNV-1a over the primitive, material and light arrays) is re-checked on load: a file whose
+// geometry section was damaged, or a reader built with another struct layout, is refused instead of rendered.
+const char kMagic[8] = { 'W', 'R', 'T', 'S', 'C', 'N', '0', '2' };
+const uint32_t kLayoutVersion = 2;
+
+uint64_t fnv1a(uint64_t h, const void* p, size_t n)
+{
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+uint64_t scene_fingerprint(const HostScene& hs)
+{
+    uint64_t h = 1469598103934665603ull;
+    h = fnv1a(h, hs.prim_kind.data(), hs.prim_kind.size() * sizeof(int32_t));
+    h = fnv1a(h, hs.prim_data.data(), hs.prim_data.size() * sizeof(float));
+    h = fnv1a(h, hs.prim_matid.data(), hs.prim_matid.size() * sizeof(int32_t));
+    h = fnv1a(h, hs.materials.data(), hs.materials.size() * sizeof(float));
+    h = fnv1a(h, hs.lights.data(), hs.lights.size() * sizeof(float));
+    return h;
+}
 template <class T> void put(FILE* f, const std::vector<T>& v)
 {
     uint64_t n = v.size();
     fwrite(&n, sizeof n, 1, f);
     if (n) fwrite(v.data(), sizeof(T), n, f);
 }
-template <class T> bool get(FILE* f, std::vector<T>& v)
+// The element count comes from the file: bound it by what is left of the file BEFORE resizing.
+template <class T> bool get(FILE* f, long file_size, std::vector<T>& v)
 {
     uint64_t n = 0;
     if (fread(&n, sizeof n, 1, f) != 1) return false;
-    v.resize(n);
+    const long at = ftell(f);
+    if (at < 0 || n > (uint64_t)(file_size - at) / sizeof(T)) return false;
+    v.resize((size_t)n);
     return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
 }
 }  // namespace
@@ -501,6 +527,10 @@ bool save_cache(const HostScene& hs, const char* path, std::string& err)
     FILE* f = fopen(path, "wb");
     if (!f) { err = std::string("cannot write ") + path; return false; }
     fwrite(kMagic, 1, 8, f);
+    const uint32_t ver[2] = { kLayoutVersion, (uint32_t)sizeof(wrt_camera) };
+    fwrite(ver, sizeof ver, 1, f);
+    const uint64_t fp = scene_fingerprint(hs);
+    fwrite(&fp, sizeof fp, 1, f);
     put(f, hs.prim_kind); put(f, hs.prim_data); put(f, hs.prim_matid); put(f, hs.materials); put(f, hs.lights);
     int32_t flags[4] = { hs.has_camera, hs.tree_built, hs.tree.dep_max, hs.tree.depth };
     fwrite(flags, sizeof flags, 1, f);
@@ -510,7 +540,9 @@ bool save_cache(const HostScene& hs, const char* path, std::string& err)
     fwrite(hs.tree.root_box, sizeof hs.tree.root_box, 1, f);
     put(f, hs.tree.axis); put(f, hs.tree.split); put(f, hs.tree.left); put(f, hs.tree.right);
     put(f, hs.tree.first_ref); put(f, hs.tree.n_ref); put(f, hs.tree.refs);
+    const bool ok = fflush(f) == 0 && !ferror(f);
     fclose(f);
+    if (!ok) { err = std::string("write error on ") + path; return false; }
     return true;
 }
 
@@ -518,20 +550,36 @@ bool load_cache(const char* path, HostScene& hs, std::string& err)
 {
     FILE* f = fopen(path, "rb");
     if (!f) { err = std::string("cannot open ") + path; return false; }
+    fseek(f, 0, SEEK_END);
+    const long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
     char magic[8];
-    bool ok = fread(magic, 1, 8, f) == 8 && memcmp(magic, kMagic, 8) == 0;
-    ok = ok && get(f, hs.prim_kind) && get(f, hs.prim_data) && get(f, hs.prim_matid) && get(f, hs.materials) && get(f, hs.lights);
+    uint32_t ver[2] = { 0, 0 };
+    uint64_t fp = 0;
+    bool ok = size > 0 && fread(magic, 1, 8, f) == 8 && memcmp(magic, kMagic, 8) == 0;
+    ok = ok && fread(ver, sizeof ver, 1, f) == 1 && ver[0] == kLayoutVersion && ver[1] == (uint32_t)sizeof(wrt_camera);
+    ok = ok && fread(&fp, sizeof fp, 1, f) == 1;
+    ok = ok && get(f, size, hs.prim_kind) && get(f, size, hs.prim_data) && get(f, size, hs.prim_matid) &&
+         get(f, size, hs.materials) && get(f, size, hs.lights);
     int32_t flags[4] = { 0, 0, 0, 0 };
     ok = ok && fread(flags, sizeof flags, 1, f) == 1;
     ok = ok && fread(hs.cam_args, sizeof hs.cam_args, 1, f) == 1;
     ok = ok && fread(&hs.camera, sizeof hs.camera, 1, f) == 1;
     ok = ok && fread(hs.scene_sphere, sizeof hs.scene_sphere, 1, f) == 1;
     ok = ok && fread(hs.tree.root_box, sizeof hs.tree.root_box, 1, f) == 1;
-    ok = ok && get(f, hs.tree.axis) && get(f, hs.tree.split) && get(f, hs.tree.left) && get(f, hs.tree.right);
-    ok = ok && get(f, hs.tree.first_ref) && get(f, hs.tree.n_ref) && get(f, hs.tree.refs);
+    ok = ok && get(f, size, hs.tree.axis) && get(f, size, hs.tree.split) && get(f, size, hs.tree.left) && get(f, size, hs.tree.right);
+    ok = ok && get(f, size, hs.tree.first_ref) && get(f, size, hs.tree.n_ref) && get(f, size, hs.tree.refs);
     fclose(f);
-    if (!ok) { err = std::string("not a wrt scene cache (or truncated): ") + path; return false; }
-    hs.has_camera = flags[0] != 0; hs.tree_built = flags[1] != 0; hs.tree.dep_max = flags[2]; hs.tree.depth = flags[3];
+    if (!ok) { err = std::string("not a wrt scene cache of this build (wrong magic / layout version, or truncated): ") + path; return false; }
+    // cross-array consistency: everything wrt_host_scene_desc / build_layout will index
+    const size_t np = hs.prim_kind.size(), nn = hs.tree.axis.size();
+    if (hs.prim_data.size() != 9 * np || hs.prim_matid.size() != np || hs.materials.size() % 11 != 0 || hs.lights.size() % 12 != 0 ||
+        hs.tree.split.size() != nn || hs.tree.left.size() != nn || hs.tree.right.size() != nn ||
+        hs.tree.first_ref.size() != nn || hs.tree.n_ref.size() != nn || np > (size_t)INT32_MAX || nn > (size_t)INT32_MAX) {
+        err = std::string("inconsistent array lengths in scene cache: ") + path; return false;
+    }
+    if (scene_fingerprint(hs) != fp) { err = std::string("scene cache fingerprint mismatch (file damaged): ") + path; return false; }
+    hs.has_camera = flags[0] != 0; hs.tree_built = flags[1] != 0 && nn > 0; hs.tree.dep_max = flags[2]; hs.tree.depth = flags[3];
     return true;
 }
 
