@@ -222,6 +222,22 @@ int wrt_render_bdpt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_par
 int wrt_film_resolve_dev(const float* d_film_hw3, int32_t width, int32_t height, float scale, float gamma,
                          uint8_t* d_rgb_hw3, void* stream);
 
+/* ---- diagnostics: how parity with the reference is checked on the device ---------------------------------- */
+/* The shading math of the bounce loops evaluated on the device, one reference function per call (`what`):
+ *   0 BSDF::f   1 BSDF::sample   2 BSDF::pdf           (R/src/material/bsdf.cpp:102-335, fresnel.cpp:3-30)
+ *   3 AreaLight::illuminance   4 ::emit   5 ::getRadiance   (R/src/scene/light.cpp:4-100)
+ *   6 fresnelDielectric   7 sampleTriangle / sampleCosHemisphere / samplePowerCosHemisphere + pdfs (sampler.cpp)
+ *   8 sample k of pixel (i, j): sampleRectangleStratified + Camera::generateRay (surfaceIntegrator.cpp:26-34; iparam = spp)
+ * `in` / `out` hold n fixed-size records; the record layouts are documented in csrc/shading_kat.cuh and are the ones
+ * oracle/ref_harness.cpp::ref_shading_batch uses for the reference's own functions.  Host buffers. */
+int wrt_debug_shading(wrt_scene* sc, const wrt_camera* cam, int what, int iparam, const float* in, size_t n, float* out);
+/* RNG replay: installs (copies) a tape of random floats; while installed, wrt_render_pt / wrt_render_bdpt draw the
+ * numbers of sample (pixel p, sample k) from tape[(p*spp + k)*stride ...] (PT) and of light / camera path p of iteration
+ * it from tape[((it*W*H + p)*2 + {0,1})*stride ...] (BDPT) instead of the counter-based generator.  With the tape the
+ * reference recorded for the same samples (oracle/ref_harness.cpp) both renderers follow the same paths, and the films
+ * can be compared per pixel without Monte-Carlo noise.  tape == NULL removes it. */
+int wrt_debug_set_rng_tape(wrt_scene* sc, const float* tape, size_t n_floats, uint32_t stride);
+
 #ifdef __cplusplus
 }
 #endif

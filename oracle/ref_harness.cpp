@@ -16,6 +16,8 @@
 #include "surfaceIntegrator/bidirPathTracing.h"
 #include "surfaceIntegrator/whitted.h"
 #include "material/bsdf.h"
+#include "material/fresnel.h"
+#include "sampler/sampler.h"
 #include <unordered_map>
 #include <vector>
 #include <cstdint>
@@ -527,6 +529,153 @@ void ref_light_emit(void* hv, int light, const float* dirRand3, const float* pos
         Vector3(posRand3[0], posRand3[1], posRand3[2]), p, d, epdf, &dpdf, &cosl);
     out12[0] = c.r; out12[1] = c.g; out12[2] = c.b; out12[3] = p.x; out12[4] = p.y; out12[5] = p.z;
     out12[6] = d.x; out12[7] = d.y; out12[8] = d.z; out12[9] = epdf; out12[10] = dpdf; out12[11] = cosl;
+}
+
+
+// ---- batched shading known-answer tests -----------------------------------------------------------------------
+// One call evaluates n inputs of one reference function; the device (wrt_debug_shading) and hostsim take the same
+// (what, in, out) layout, so the three can be compared entry by entry.  in/out strides are fixed per `what`:
+//   0 BSDF::f            in 10: wi3 n3 matid wo3         out 9: f.rgb cosWo dirPdf revPdf continueProb isDelta valid
+//   1 BSDF::sample       in 10: wi3 n3 matid rand3       out 9: f.rgb wo3 pdf cosWo type
+//   2 BSDF::pdf          in 10: wi3 n3 matid wo3         out 2: pdf, reverse pdf
+//   3 AreaLight::illuminance  in 7: light pos3 rand3     out 10: illu.rgb dir3 dist directPdf emissionPdf cosAtLight
+//   4 AreaLight::emit    in 7: light dirRand3 posRand3   out 12: energy.rgb pos3 dir3 emissionPdf directPdfArea cosAtLight
+//   5 AreaLight::getRadiance  in 4: light dir3           out 5: rad.rgb directPdfArea emissionPdf
+//   6 fresnelDielectric  in 2: cosI index                out 1
+//   7 samplers           in 13: rand3 power v1 v2 v3     out 13: sampleTriangle p3 | sampleCosHemisphere dir3 pdf |
+//                                                                 samplePowerCosHemisphere dir3 | cosHemispherePdf(z, cos dir) |
+//                                                                 powerCosHemispherePdf(z, power dir, power) | 0
+//   8 camera sample      in 5: rand.x rand.y i j k       out 8: the Ray of SurfaceIntegrator::render's sample k of pixel (i, j)
+//                        (sampleRectangleStratified + Camera::generateRay; spp = `iparam`)
+int ref_shading_in_stride(int what) { static const int s[9] = { 10, 10, 10, 7, 7, 4, 2, 13, 5 }; return what >= 0 && what < 9 ? s[what] : 0; }
+int ref_shading_out_stride(int what) { static const int s[9] = { 9, 9, 2, 10, 12, 5, 1, 13, 8 }; return what >= 0 && what < 9 ? s[what] : 0; }
+
+int ref_shading_batch(void* hv, int what, int iparam, const float* in, long long n, float* out)
+{
+    RefHandle* h = (RefHandle*)hv;
+    Scene& sc = h->scene();
+    const int is = ref_shading_in_stride(what), os = ref_shading_out_stride(what);
+    if (!is) return -1;
+    for (long long e = 0; e < n; e++) {
+        const float* a = in + (size_t)is * e;
+        float* o = out + (size_t)os * e;
+        for (int k = 0; k < os; k++) o[k] = 0.f;
+        if (what <= 2) {
+            Intersection inter; inter.t = 1.f; inter.p = Vector3(0.f); inter.n = Vector3(a[3], a[4], a[5]);
+            inter.inside = 0; inter.matId = (int)a[6];
+            BSDF b(Vector3(a[0], a[1], a[2]), inter, sc);
+            if (what == 0) {
+                o[8] = b.isValid() ? 1.f : 0.f;
+                if (!b.isValid() || inter.matId <= 0) continue;
+                Real cosWo = 0, dp = 0, rp = 0;
+                Color3 f = b.f(sc, Vector3(a[7], a[8], a[9]), cosWo, &dp, &rp);
+                o[0] = f.r; o[1] = f.g; o[2] = f.b; o[3] = cosWo; o[4] = dp; o[5] = rp;
+                o[6] = b.continueProb; o[7] = b.isDelta ? 1.f : 0.f;
+            } else if (what == 1) {
+                if (!b.isValid() || inter.matId <= 0) continue;
+                Vector3 wo(0.f); Real pdf = 0, cosWo = 0; int type = 0;
+                Color3 f = b.sample(sc, Vector3(a[7], a[8], a[9]), wo, pdf, cosWo, &type);
+                o[0] = f.r; o[1] = f.g; o[2] = f.b; o[3] = wo.x; o[4] = wo.y; o[5] = wo.z; o[6] = pdf; o[7] = cosWo; o[8] = (float)type;
+            } else {
+                if (!b.isValid() || inter.matId <= 0) continue;
+                o[0] = b.pdf(sc, Vector3(a[7], a[8], a[9]), false);
+                o[1] = b.pdf(sc, Vector3(a[7], a[8], a[9]), true);
+            }
+        } else if (what == 3) {
+            Vector3 d(0.f); Real dist = 0, dpdf = 0, epdf = 0, cosl = 0;
+            Color3 c = sc.lights[(int)a[0]]->illuminance(sc.sceneSphere, Vector3(a[1], a[2], a[3]), Vector3(a[4], a[5], a[6]), d, dist, dpdf, &epdf, &cosl);
+            o[0] = c.r; o[1] = c.g; o[2] = c.b; o[3] = d.x; o[4] = d.y; o[5] = d.z; o[6] = dist; o[7] = dpdf; o[8] = epdf; o[9] = cosl;
+        } else if (what == 4) {
+            Vector3 p(0.f), d(0.f); Real epdf = 0, dpdf = 0, cosl = 0;
+            Color3 c = sc.lights[(int)a[0]]->emit(sc.sceneSphere, Vector3(a[1], a[2], a[3]), Vector3(a[4], a[5], a[6]), p, d, epdf, &dpdf, &cosl);
+            o[0] = c.r; o[1] = c.g; o[2] = c.b; o[3] = p.x; o[4] = p.y; o[5] = p.z; o[6] = d.x; o[7] = d.y; o[8] = d.z; o[9] = epdf; o[10] = dpdf; o[11] = cosl;
+        } else if (what == 5) {
+            Real dpa = 0, epdf = 0;
+            Color3 c = sc.lights[(int)a[0]]->getRadiance(sc.sceneSphere, Vector3(a[1], a[2], a[3]), Vector3(0.f), &dpa, &epdf);
+            o[0] = c.r; o[1] = c.g; o[2] = c.b; o[3] = dpa; o[4] = epdf;
+        } else if (what == 6) {
+            o[0] = fresnelDielectric(a[0], a[1]);
+        } else if (what == 7) {
+            const Vector3 r(a[0], a[1], a[2]);
+            Vector3 p = sampleTriangle(r, Vector3(a[4], a[5], a[6]), Vector3(a[7], a[8], a[9]), Vector3(a[10], a[11], a[12]));
+            o[0] = p.x; o[1] = p.y; o[2] = p.z;
+            Real pdf = 0;
+            Vector3 c = sampleCosHemisphere(r, &pdf);
+            o[3] = c.x; o[4] = c.y; o[5] = c.z; o[6] = pdf;
+            Vector3 g = samplePowerCosHemisphere(r, a[3], NULL);
+            o[7] = g.x; o[8] = g.y; o[9] = g.z;
+            o[10] = cosHemispherePdf(Vector3(0.f, 0.f, 1.f), c);
+            o[11] = powerCosHemispherePdf(Vector3(0.f, 0.f, 1.f), g, a[3]);
+        } else if (what == 8) {
+            const int i = (int)a[2], j = (int)a[3], k = (int)a[4];
+            Vector3 v0 = Vector3(j - 0.5f, i - 0.5f, 0), v1 = Vector3(j + 0.5f, i - 0.5f, 0), v2 = Vector3(j - 0.5f, i + 0.5f, 0);
+            Vector3 pr = sampleRectangleStratified(Vector3(a[0], a[1], 0.f), v0, v1, v2, k, iparam);
+            Ray r = sc.camera.generateRay(pr.x, pr.y);
+            o[0] = r.origin.x; o[1] = r.origin.y; o[2] = r.origin.z; o[3] = r.dir.x; o[4] = r.dir.y; o[5] = r.dir.z; o[6] = r.tmin; o[7] = r.tmax;
+        }
+    }
+    return 0;
+}
+
+// Scene::shadowRayTest(ray, p) (scene.cpp:55-69) and bool Scene::intersect(ray) (scene.cpp:45-53) on batches of
+// already-constructed rays.
+void ref_shadow_test(void* hv, const float* rays8, const float* target3, long long n, float* visible)
+{
+    Scene& sc = ((RefHandle*)hv)->scene();
+    for (long long i = 0; i < n; i++) {
+        Ray r = make_ray(rays8 + 8 * i);
+        visible[i] = sc.shadowRayTest(r, Vector3(target3[3 * i], target3[3 * i + 1], target3[3 * i + 2]));
+    }
+}
+
+void ref_intersect_any(void* hv, const float* rays8, long long n, unsigned char* hit)
+{
+    Scene& sc = ((RefHandle*)hv)->scene();
+    for (long long i = 0; i < n; i++) { Ray r = make_ray(rays8 + 8 * i); hit[i] = sc.intersect(r) ? 1 : 0; }
+}
+
+// ---- random-number tapes: same random numbers for the reference and the device ------------------------------------
+// The reference draws every number of a render from ONE MT19937 stream, sample after sample.  These entry points run the
+// unmodified per-sample code and record, for every sample, the `stride` floats the stream holds from the point where
+// the sample starts (a sample consumes a prefix of them).  The device integrators replay the tape (wrt_debug_set_rng_tape),
+// so both sides follow the SAME path sample for sample and the films can be compared per pixel, without Monte-Carlo noise.
+static void tape_record(const RNG& at, int stride, float* dst)
+{
+    RNG copy = at;                      // 624 words + index: the stream from here on
+    for (int k = 0; k < stride; k++) dst[k] = copy.randFloat();
+}
+static inline int stream_pos(const RNG& r) { return r.mti % RNG::N; }
+
+// PathIntegrator: SurfaceIntegrator::render()'s loop (surfaceIntegrator.cpp:17-45) with the recorder around each sample.
+// tape: [H*W*spp][stride]; sample_rgb: [H*W*spp][3] (raytracing()'s return value per sample); draws: [H*W*spp].
+int ref_render_pt_tape(void* hv, int spp, int max_depth, unsigned seed, int stride, float* tape, float* sample_rgb,
+                       int* draws, float* film)
+{
+    RefHandle* h = (RefHandle*)hv;
+    if (h->kind != 0) return -1;
+    PathIntegrator* in = h->pt;
+    in->samplesPerPixel = spp; in->maxTracingDepth = max_depth;
+    in->rng.seed(seed); in->rng.mti = RNG::N;
+    clear_film(in->film);
+    size_t s = 0;
+    for (int i = 0; i < in->height; i++)
+        for (int j = 0; j < in->width; j++)
+            for (int k = 0; k < spp; k++, s++) {
+                tape_record(in->rng, stride, tape + s * (size_t)stride);
+                const int p0 = stream_pos(in->rng);
+                Vector3 v0 = Vector3(j - 0.5f, i - 0.5f, 0);
+                Vector3 v1 = Vector3(j + 0.5f, i - 0.5f, 0);
+                Vector3 v2 = Vector3(j - 0.5f, i + 0.5f, 0);
+                Vector3 posRaster = sampleRectangleStratified(in->rng.randVector3(), v0, v1, v2, k, spp);
+                Ray ray = in->scene.camera.generateRay(posRaster.x, posRaster.y);
+                Color3 tmp = in->raytracing(ray, 0);
+                in->film->addColor(i, j, tmp);
+                if (sample_rgb) { sample_rgb[3 * s] = tmp.r; sample_rgb[3 * s + 1] = tmp.g; sample_rgb[3 * s + 2] = tmp.b; }
+                if (draws) draws[s] = (stream_pos(in->rng) - p0 + RNG::N) % RNG::N;
+            }
+    in->film->scale(1.f / spp);
+    if (film) copy_film(in->film, film);
+    return 0;
 }
 
 // MT19937 stream of the reference RNG (R/src/math/rng.cpp): n floats after seeding.

@@ -12,9 +12,11 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libwrt_ref.so")
+HOOKS_SO = os.path.join(_HERE, "_ref", "libwrt_ref_hooks.so")
 REF_ROOT = "/root/reference/Winmad-s-raytracer-v1.0"
 
 _lib = None
+_hooks = None
 
 
 def available():
@@ -29,12 +31,22 @@ def lib():
         cwd = os.getcwd()
         scratch = tempfile.mkdtemp(prefix="wrt_ref_")
         os.chdir(scratch)
+        global _hooks
         try:
+            # the interposer first, globally visible: libwrt_ref.so's PLT calls to generateLightSample /
+            # generateCameraSample then bind to it (ref_hooks.cpp); lazy binding lets its own RNG references wait
+            if os.path.exists(HOOKS_SO):
+                _hooks = C.CDLL(HOOKS_SO, mode=C.RTLD_GLOBAL | os.RTLD_LAZY)
             _lib = C.CDLL(REF_SO)
         finally:
             os.chdir(cwd)
         _lib.ref_create.restype = C.c_void_p
         _lib.ref_traverse_calls.restype = C.c_ulonglong
+        if _hooks is not None:
+            real = [C.cast(getattr(_lib, n), C.c_void_p) for n in
+                    ("_ZN16BidirPathTracing19generateLightSampleER14BidirPathState",
+                     "_ZN16BidirPathTracing20generateCameraSampleEiR14BidirPathState")]
+            _hooks.ref_hooks_set_real(real[0], real[1])
     return _lib
 
 
@@ -185,6 +197,63 @@ class RefScene:
         assert self.L.ref_render_bdpt(self.h, iterations, C.c_uint(seed), control_length,
                                       max_path_length, _fp(f)) == 0
         return f
+
+    # -- shading known-answer batches, shadow / any-hit queries, RNG tapes (ref_harness.cpp) ------------
+    SHADING_IN = {0: 10, 1: 10, 2: 10, 3: 7, 4: 7, 5: 4, 6: 2, 7: 13, 8: 5}
+    SHADING_OUT = {0: 9, 1: 9, 2: 2, 3: 10, 4: 12, 5: 5, 6: 1, 7: 13, 8: 8}
+
+    def shading(self, what, inputs, iparam=0):
+        a = np.ascontiguousarray(inputs, np.float32).reshape(-1, self.SHADING_IN[what])
+        out = np.zeros((len(a), self.SHADING_OUT[what]), np.float32)
+        assert self.L.ref_shading_batch(self.h, int(what), int(iparam), _fp(a), C.c_longlong(len(a)), _fp(out)) == 0
+        return out
+
+    def shadow_test(self, rays8, target3):
+        r = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)
+        p = np.ascontiguousarray(target3, np.float32).reshape(-1, 3)
+        vis = np.zeros(len(r), np.float32)
+        self.L.ref_shadow_test(self.h, _fp(r), _fp(p), C.c_longlong(len(r)), _fp(vis))
+        return vis
+
+    def intersect_any(self, rays8):
+        r = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)
+        hit = np.zeros(len(r), np.uint8)
+        self.L.ref_intersect_any(self.h, _fp(r), C.c_longlong(len(r)), hit.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return hit
+
+    def render_pt_tape(self, spp, max_depth, seed=5489, stride=96):
+        """The unmodified per-sample code with a recorder around every sample: returns (film, tape[n][stride],
+        sample_rgb[n][3], draws[n]) with n = H*W*spp in the render loop's order (pixel-major, then sample)."""
+        n = self.height * self.width * spp
+        tape = np.zeros((n, stride), np.float32); rgb = np.zeros((n, 3), np.float32); draws = np.zeros(n, np.int32)
+        film = np.zeros((self.height, self.width, 3), np.float32)
+        assert self.L.ref_render_pt_tape(self.h, spp, max_depth, C.c_uint(seed), stride, _fp(tape), _fp(rgb), _ip(draws), _fp(film)) == 0
+        assert draws.max() <= stride, "tape stride too short: a sample drew %d numbers" % draws.max()
+        return film, tape, rgb, draws
+
+    def render_bdpt_tape(self, iterations, seed=5489, stride=160, control_length=3, max_path_length=10):
+        """BidirPathTracing::render() with the interposed recorder (ref_hooks.cpp): returns (raw film, tape, draws) where
+        tape[(it*W*H + p)*2 + {0: light, 1: camera}][stride] holds the stream at the start of that path and draws the
+        numbers each path consumed (the last camera path's count is unknown: -1)."""
+        lib()
+        assert _hooks is not None, "oracle/_ref/libwrt_ref_hooks.so not built"
+        paths = self.width * self.height * iterations
+        tape = np.zeros((2 * paths, stride), np.float32)
+        pos = np.zeros(2 * paths, np.int64)
+        _hooks.ref_hooks_start(_fp(tape), stride, C.c_longlong(paths), pos.ctypes.data_as(C.POINTER(C.c_longlong)))
+        try:
+            film = self.render_bdpt(iterations, seed=seed, control_length=control_length, max_path_length=max_path_length)
+        finally:
+            lc, cc = C.c_longlong(), C.c_longlong()
+            _hooks.ref_hooks_stop(C.byref(lc), C.byref(cc))
+        assert lc.value == paths and cc.value == paths, "hooks saw %d light / %d camera paths, expected %d" % (lc.value, cc.value, paths)
+        # order of execution: per iteration all light paths, then all camera paths
+        npix = self.width * self.height
+        order = np.concatenate([np.concatenate([(np.arange(npix) + it * npix) * 2, (np.arange(npix) + it * npix) * 2 + 1]) for it in range(iterations)])
+        draws = np.full(2 * paths, -1, np.int64)
+        draws[order[:-1]] = pos[order[1:]] - pos[order[:-1]]
+        assert draws.max() <= stride, "tape stride too short: a path drew %d numbers" % draws.max()
+        return film, tape, draws
 
     def traverse_calls(self):
         return int(self.L.ref_traverse_calls())

@@ -11,6 +11,7 @@
 #include "pt_logic.cuh"
 #include "bdpt_logic.cuh"
 #include "whitted_logic.cuh"
+#include "shading_kat.cuh"
 
 using namespace wrt;
 
@@ -50,6 +51,20 @@ int hs_scene_create(const wrt_scene_desc* d, void** out, char* err256)
 }
 
 void hs_scene_destroy(void* h) { delete (HsScene*)h; }
+
+// RNG replay (shading.cuh): the host build reads the tape through h_rng_tape; stride 0 / null removes it.
+static uint32_t g_tape_stride = 0;
+void hs_set_rng_tape(const float* tape, unsigned stride) { h_rng_tape = tape; g_tape_stride = tape ? stride : 0; }
+
+// The shading known-answer entry (csrc/shading_kat.cuh) on the CPU build of the same code.
+void hs_debug_shading(void* hv, const wrt_camera* cam, int what, int iparam, const float* in, size_t n, float* out)
+{
+    const DevSceneView& sc = ((HsScene*)hv)->L.view;
+    DevCamera dc; memset(&dc, 0, sizeof dc);
+    if (cam) cam_fill(cam, dc);
+    const int is = shading_kat_in_stride(what), os = shading_kat_out_stride(what);
+    for (size_t e = 0; e < n; e++) shading_kat(sc, dc, what, iparam, in + (size_t)is * e, out + (size_t)os * e);
+}
 
 int hs_num_nodes(void* h) { return ((HsScene*)h)->L.n_nodes; }
 long long hs_num_recs(void* h) { return ((HsScene*)h)->L.n_recs; }
@@ -131,6 +146,7 @@ void hs_render_whitted(void* hv, const wrt_camera* cam, const wrt_pt_params* p, 
     P.local_spp = (P.spp - P.sample_first + P.sample_stride - 1) / P.sample_stride;
     P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->spp;
     P.total_samples = (unsigned long long)P.width * P.height * (unsigned long long)P.local_spp;
+    P.tape_stride = g_tape_stride;
     DevCamera dc; cam_fill(cam, dc);
     unsigned long long nrays = 0;
     struct Item { RayIn r; float w; int dep; };
@@ -177,6 +193,7 @@ void hs_render_pt(void* hv, const wrt_camera* cam, const wrt_pt_params* p, int p
     P.local_spp = (P.spp - P.sample_first + P.sample_stride - 1) / P.sample_stride;
     P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->spp;
     P.total_samples = (unsigned long long)P.width * P.height * (unsigned long long)P.local_spp;
+    P.tape_stride = g_tape_stride;
     DevCamera dc; cam_fill(cam, dc);
     unsigned long long nrays = 0;
     for (unsigned long long s = 0; s < P.total_samples; s++) {
@@ -217,6 +234,7 @@ void hs_render_bdpt(void* hv, const wrt_camera* cam, const wrt_bdpt_params* p, i
     P.n_paths = (unsigned)(p->width * p->height); P.light_path_num = (float)(p->width * p->height);
     P.n_pixels = P.n_paths; P.iter_stride = 1;      // one iteration at a time here; the kernels batch several
     P.trace_gated = 1;
+    P.tape_stride = g_tape_stride;
     const int stride = p->iter_stride > 0 ? p->iter_stride : 1;
     const int maxv = P.max_len > 1 ? P.max_len - 1 : 1;
     unsigned long long nrays = 0;

@@ -86,6 +86,24 @@ class HostSim:
                              C.byref(rays))
         return film, rays.value
 
+    def debug_shading(self, what, inputs, iparam=0, cam=None):
+        IN = {0: 10, 1: 10, 2: 10, 3: 7, 4: 7, 5: 4, 6: 2, 7: 13, 8: 5}
+        OUT = {0: 9, 1: 9, 2: 2, 3: 10, 4: 12, 5: 5, 6: 1, 7: 13, 8: 8}
+        a = np.ascontiguousarray(inputs, np.float32).reshape(-1, IN[what])
+        out = np.zeros((len(a), OUT[what]), np.float32)
+        lib().hs_debug_shading(self.h, C.byref(cam) if cam is not None else None, int(what), int(iparam),
+                               a.ctypes.data_as(C.c_void_p), C.c_size_t(len(a)), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def set_rng_tape(self, tape, stride=0):
+        """RNG replay for the next renders of ANY HostSim (process-global, like the device's per-scene tape)."""
+        if tape is None:
+            self._tape = None
+            lib().hs_set_rng_tape(None, 0)
+            return
+        self._tape = np.ascontiguousarray(tape, np.float32).ravel()
+        lib().hs_set_rng_tape(self._tape.ctypes.data_as(C.c_void_p), C.c_uint(int(stride)))
+
     def __del__(self):
         try:
             lib().hs_scene_destroy(self.h)

@@ -95,6 +95,7 @@ EXPORTS = [
     "wrt_reset_stats", "wrt_trace_closest", "wrt_trace_closest_full", "wrt_trace_any", "wrt_trace_shadow",
     "wrt_trace_occluded", "wrt_trace_closest_dev", "wrt_trace_occluded_dev", "wrt_trace_count_visits",
     "wrt_render_pt", "wrt_render_pt_dev", "wrt_render_whitted", "wrt_render_whitted_dev", "wrt_render_bdpt", "wrt_render_bdpt_dev", "wrt_film_resolve_dev",
+    "wrt_debug_shading", "wrt_debug_set_rng_tape",
 ]
 
 _lib = None
@@ -433,6 +434,24 @@ class Scene:
     def render_bdpt_dev(self, cam, params, d_film, stream=None):
         _check(lib().wrt_render_bdpt_dev(self._sc, C.byref(cam), C.byref(params), C.c_void_p(d_film),
                                          C.c_void_p(stream or 0)), "wrt_render_bdpt_dev")
+
+    # diagnostics (include/wrt.h): shading known-answer evaluation and RNG replay
+    SHADING_IN = {0: 10, 1: 10, 2: 10, 3: 7, 4: 7, 5: 4, 6: 2, 7: 13, 8: 5}
+    SHADING_OUT = {0: 9, 1: 9, 2: 2, 3: 10, 4: 12, 5: 5, 6: 1, 7: 13, 8: 8}
+
+    def debug_shading(self, what, inputs, iparam=0, cam=None):
+        a = _f32(inputs, (-1, self.SHADING_IN[what])); n = len(a)
+        out = np.zeros((n, self.SHADING_OUT[what]), np.float32)
+        _check(lib().wrt_debug_shading(self._sc, C.byref(cam) if cam is not None else None, int(what), int(iparam),
+                                       _ptr(a, _f32p), C.c_size_t(n), _ptr(out, _f32p)), "wrt_debug_shading")
+        return out
+
+    def set_rng_tape(self, tape, stride):
+        if tape is None:
+            _check(lib().wrt_debug_set_rng_tape(self._sc, None, C.c_size_t(0), C.c_uint32(0)), "wrt_debug_set_rng_tape")
+            return
+        t = _f32(tape).ravel()
+        _check(lib().wrt_debug_set_rng_tape(self._sc, _ptr(t, _f32p), C.c_size_t(len(t)), C.c_uint32(int(stride))), "wrt_debug_set_rng_tape")
 
     def close(self):
         if self._sc:

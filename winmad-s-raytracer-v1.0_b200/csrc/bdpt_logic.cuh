@@ -33,6 +33,7 @@ struct BdptParams {
     unsigned n_pixels;        // width * height: paths per iteration
     unsigned n_paths;         // path slots of this batch = (iterations in the batch) * n_pixels
     int trace_gated;          // 1: also trace connection rays whose contribution is gated out (as the reference does)
+    uint32_t tape_stride;     // > 0: RNG replay; light path p of iteration it reads tape[((it*n_pixels + p)*2 + 0)*stride ...], camera path + 1
 };
 
 struct BdptPath {             // BidirPathState without its BSDF / origin / dir (those live in the ray)
@@ -74,7 +75,7 @@ WRT_HD void bdpt_light_generate(const DevSceneView& sc, const BdptParams& P, uin
     // path p only reads light path p of its own iteration, bidirPathTracing.cpp:222-229)
     const uint32_t within = index % P.n_pixels;
     const unsigned long long iter = (unsigned long long)P.iteration + (unsigned long long)(index / P.n_pixels) * (unsigned)P.iter_stride;
-    st.rng = rng_make(P.seed, 1u, iter * P.n_pixels + within);
+    st.rng = P.tape_stride ? rng_make_tape((iter * P.n_pixels + within) * 2ull, P.tape_stride) : rng_make(P.seed, 1u, iter * P.n_pixels + within);
     const int nl = sc.n_lights;
     const float pick = 1.f / nl;
     int lid = (int)(rng_float(st.rng) * nl);
@@ -82,7 +83,10 @@ WRT_HD void bdpt_light_generate(const DevSceneView& sc, const BdptParams& P, uin
     V3 pos = v3(0, 0, 0), dir = v3(0, 0, 1), rad = v3(0, 0, 0);
     float epdf = 0.f, dpdf = 0.f, cosl = 0.f;
     for (int tries = 0; tries < 64; tries++) {     // reference: for(;;) until emissionPdf > 1e-7
-        const V3 dr = rng_vec3(st.rng), pr = rng_vec3(st.rng);
+        // light->emit(sphere, rng.randVector3(), rng.randVector3(), ...) (:282-285): the order of the two draws is the
+        // compiler's choice; g++ on x86-64 evaluates arguments right to left, so the POSITION numbers come first
+        // (checked by the RNG-tape tests, which replay the compiled reference's stream)
+        const V3 pr = rng_vec3(st.rng), dr = rng_vec3(st.rng);
         rad = light_emit(sc.lights[lid], dr, pr, pos, dir, epdf, dpdf, cosl);
         if (epdf > 1e-7f) break;
     }
@@ -100,7 +104,7 @@ WRT_HD void bdpt_camera_generate(const BdptParams& P, const DevCamera& cam, uint
 {
     const uint32_t within = index % P.n_pixels;
     const unsigned long long iter = (unsigned long long)P.iteration + (unsigned long long)(index / P.n_pixels) * (unsigned)P.iter_stride;
-    st.rng = rng_make(P.seed, 2u, iter * P.n_pixels + within);
+    st.rng = P.tape_stride ? rng_make_tape((iter * P.n_pixels + within) * 2ull + 1ull, P.tape_stride) : rng_make(P.seed, 2u, iter * P.n_pixels + within);
     const int y = (int)(within % (uint32_t)P.width), x = (int)(within / (uint32_t)P.width);
     const V3 j = rng_vec3(st.rng);
     const float sx = (float)x + j.x, sy = (float)y + j.y;

@@ -297,6 +297,19 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
     P.n_paths = P.n_pixels;
     P.light_path_num = (float)(p->width * p->height);
     { const char* e = getenv("WRT_BDPT_SKIP_GATED"); P.trace_gated = (e && atoi(e)) ? 0 : 1; }
+    P.tape_stride = 0;
+    struct TapeGuard {
+        bool on = false;
+        ~TapeGuard() { if (on) { const float* none = nullptr; cudaMemcpyToSymbol(c_rng_tape, &none, sizeof none); } }
+    } tape_guard;
+    if (sc->d_rng_tape) {      // diagnostics: replay the reference's random numbers (wrt_debug_set_rng_tape)
+        const unsigned long long need = 2ull * P.n_pixels * (unsigned long long)p->iterations * sc->rng_tape_stride;
+        if (need > sc->rng_tape_floats) { set_error("wrt_render_bdpt: the installed RNG tape is shorter than 2*width*height*iterations*stride"); return WRT_ERR_INVALID; }
+        const float* tp = sc->d_rng_tape;
+        WRT_CUDA(cudaMemcpyToSymbol(c_rng_tape, &tp, sizeof tp));
+        tape_guard.on = true;
+        P.tape_stride = sc->rng_tape_stride;
+    }
     const int stride = p->iter_stride > 0 ? p->iter_stride : 1;
     if (p->iter_first < 0 || p->iter_first >= p->iterations) { set_error("wrt_render_bdpt: iter_first out of range"); return WRT_ERR_INVALID; }
     P.iter_stride = stride;

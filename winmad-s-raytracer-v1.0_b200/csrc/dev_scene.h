@@ -84,6 +84,7 @@ struct wrt_scene {
     wrt_trace_ctx trace_ctx[WRT_MAX_TRACE_STREAMS]; int n_trace_ctx;   // device-pointer entry points: one per caller stream
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev_fork;
+    float* d_rng_tape; size_t rng_tape_floats; uint32_t rng_tape_stride;   // diagnostics: RNG replay (wrt_debug_set_rng_tape)
     struct wrt_wavefront* wf;        // lazily created integrator state (sub-pool 0; owns the film and BDPT buffers)
     struct wrt_wavefront* wf_extra[7]; // further PT sub-pools (each with its own stream), see pt_wavefront.cu
 };

@@ -15,6 +15,7 @@ struct PtParams {
     int sample_first, sample_stride, local_spp;   // this call renders local_spp samples per pixel
     float film_scale;
     unsigned long long total_samples;             // width*height*local_spp
+    uint32_t tape_stride;                         // > 0: RNG replay, sample (pixel, k) reads tape[(pixel*spp + k)*stride ...]
 };
 
 struct PathData {      // per-path state besides the ray
@@ -34,6 +35,19 @@ struct ShadeOut {
     float q[9];
 };
 
+// Sample k of pixel (row i, column j): sampleRectangleStratified over [j-1/2, j+1/2] x [i-1/2, i+1/2] on a
+// strata x strata grid (sampler.cpp:28-42; v0 + p1*a + p2*b with p1 = (1,0,0), p2 = (0,1,0)) + Camera::generateRay.
+WRT_HD void pt_sample_ray(int strata, const DevCamera& cam, int i, int j, int k, float ux, float uy, RayIn& ray)
+{
+    const int len = strata;
+    const int row = k / len, col = k % len;
+    const float a = (ux + row) / (float)len;
+    const float b = (uy + col) / (float)len;
+    const float x = (j - 0.5f) + 1.f * a + 0.f * b;
+    const float y = (i - 0.5f) + 0.f * a + 1.f * b;
+    camera_ray(cam, x, y, ray);
+}
+
 // One camera sample: stratified jitter (sampler.cpp:28-42) + Camera::generateRay.
 WRT_HD void pt_generate(const PtParams& P, const DevCamera& cam, unsigned long long s, RayIn& ray, PathData& pd)
 {
@@ -51,15 +65,10 @@ WRT_HD void pt_generate(const PtParams& P, const DevCamera& cam, unsigned long l
         i = (int)(lin / (uint32_t)P.width); j = (int)(lin % (uint32_t)P.width);
     }
     const uint32_t pixel = (uint32_t)i * (uint32_t)P.width + (uint32_t)j;
-    pd.rng = rng_make(P.seed, 0u, (unsigned long long)k * npix + pixel);
+    pd.rng = P.tape_stride ? rng_make_tape((unsigned long long)pixel * (unsigned)P.spp + (unsigned)k, P.tape_stride)
+                           : rng_make(P.seed, 0u, (unsigned long long)k * npix + pixel);
     const V3 u = rng_vec3(pd.rng);
-    const int len = P.strata;
-    const int row = k / len, col = k % len;
-    const float a = (u.x + row) / (float)len;
-    const float b = (u.y + col) / (float)len;
-    const float x = (j - 0.5f) + 1.f * a + 0.f * b;
-    const float y = (i - 0.5f) + 0.f * a + 1.f * b;
-    camera_ray(cam, x, y, ray);
+    pt_sample_ray(P.strata, cam, i, j, k, u.x, u.y, ray);
     pd.weight = v3(1.f, 1.f, 1.f);
     pd.last_pdf = 1.f;
     pd.pixel = pixel;

@@ -337,6 +337,7 @@ static int pt_fill_params(const wrt_pt_params* p, PtParams& P)
     P.local_spp = (P.spp - P.sample_first + P.sample_stride - 1) / P.sample_stride;
     P.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->spp;
     P.total_samples = (unsigned long long)P.width * P.height * (unsigned long long)P.local_spp;
+    P.tape_stride = 0;
     return WRT_OK;
 }
 
@@ -395,6 +396,19 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         set_error("wrt_render_whitted: max_depth > 63 is not supported (the ray tree's pending list has 64 levels)"); return WRT_ERR_INVALID;
     }
     DevCamera dc; fill_camera(cam, dc);
+    // diagnostics: replay the reference's random numbers (wrt_debug_set_rng_tape)
+    struct TapeGuard {
+        bool on = false;
+        ~TapeGuard() { if (on) { const float* none = nullptr; cudaMemcpyToSymbol(c_rng_tape, &none, sizeof none); } }
+    } tape_guard;
+    if (sc->d_rng_tape) {
+        const unsigned long long need = (unsigned long long)P.width * P.height * (unsigned long long)P.spp * sc->rng_tape_stride;
+        if (need > sc->rng_tape_floats) { set_error("wrt_render_pt: the installed RNG tape is shorter than width*height*spp*stride"); return WRT_ERR_INVALID; }
+        const float* tp = sc->d_rng_tape;
+        WRT_CUDA(cudaMemcpyToSymbol(c_rng_tape, &tp, sizeof tp));
+        tape_guard.on = true;
+        P.tape_stride = sc->rng_tape_stride;
+    }
     PtPlan plan; pt_plan(P, plan, whitted);
     SubState sub[8];
     const int wh_levels = std::min(P.max_depth + 1, 64);

@@ -123,6 +123,7 @@ void wrt_scene_destroy(wrt_scene* sc)
     cudaFree(sc->d_nodes); cudaFree(sc->d_leaf_recs); cudaFree(sc->d_prims);
     cudaFree(sc->d_materials); cudaFree(sc->d_lights);
     cudaFree(sc->d_scratch_in); cudaFree(sc->d_scratch_out); cudaFree(sc->d_counters); cudaFree(sc->d_trav_scratch);
+    cudaFree(sc->d_rng_tape);
     for (int i = 0; i < sc->n_trace_ctx; i++) { cudaFree(sc->trace_ctx[i].counter); cudaFree(sc->trace_ctx[i].scratch); }
     if (sc->stream) cudaStreamDestroy(sc->stream);
     if (sc->ev0) cudaEventDestroy(sc->ev0);

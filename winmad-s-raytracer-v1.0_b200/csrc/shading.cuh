@@ -65,7 +65,29 @@ WRT_HD Rng rng_make(uint32_t seed, uint32_t stream, uint64_t sample_id)
     return r;
 }
 WRT_HD uint32_t rng_u32(Rng& r) { uint32_t c = r.ctr++; return hash32(r.key ^ hash32(c * 0x9E3779B9u + 0x6A09E667u)); }
-WRT_HD float rng_float(Rng& r) { return (float)(rng_u32(r) & 0xffffffu) / 16777216.f; }
+
+// Replay mode (diagnostics, wrt_debug_set_rng_tape): when a tape is installed, stream `key` reads its numbers from
+// tape[key + ctr] instead of hashing — the tape holds, per sample, the floats the reference's MT19937 stream delivered
+// to that sample, so the device follows the reference's paths sample for sample (tests/test_*tape*).
+#if defined(__CUDACC__)
+static __constant__ const float* c_rng_tape = nullptr;    // one copy per translation unit, set by its own entry points
+#endif
+static const float* h_rng_tape = nullptr;                 // host builds of this code (tests/hostsim)
+WRT_HD const float* rng_tape()
+{
+#ifdef __CUDA_ARCH__
+    return c_rng_tape;
+#else
+    return h_rng_tape;
+#endif
+}
+WRT_HD Rng rng_make_tape(uint64_t sample_index, uint32_t stride) { Rng r; r.key = (uint32_t)(sample_index * stride); r.ctr = 0; return r; }
+WRT_HD float rng_float(Rng& r)
+{
+    const float* tape = rng_tape();
+    if (tape) return tape[(size_t)r.key + r.ctr++];
+    return (float)(rng_u32(r) & 0xffffffu) / 16777216.f;
+}
 WRT_HD V3 rng_vec3(Rng& r) { float a = rng_float(r), b = rng_float(r), c = rng_float(r); return v3(a, b, c); }
 
 // ---- Frame ------------------------------------------------------------------------------------------

@@ -314,37 +314,56 @@ M4 mul(const M4& a, const M4& b)  // operator*, transform.cpp:27-37
     return r;
 }
 
-// General 4x4 inverse through 2x2 sub-determinants (adjugate / determinant).
+// inverse(Matrix4x4), transform.cpp:48-173: adjugate / determinant with every cofactor written as six signed triple
+// products summed left to right.  Camera matrices must be BIT-identical to the reference's (primary rays of scenes with
+// coordinates in the thousands move by whole ulps otherwise), so the term order of the reference is kept as a table:
+// inv[k] = sum over t of sign * (m[a] * m[b]) * m[c], k and a, b, c indexing the row-major 16 floats.
+const signed char kCofactor[16][6][4] = {
+    { { 1, 5,10,15}, {-1, 5,11,14}, {-1, 9, 6,15}, { 1, 9, 7,14}, { 1,13, 6,11}, {-1,13, 7,10} },
+    { {-1, 1,10,15}, { 1, 1,11,14}, { 1, 9, 2,15}, {-1, 9, 3,14}, {-1,13, 2,11}, { 1,13, 3,10} },
+    { { 1, 1, 6,15}, {-1, 1, 7,14}, {-1, 5, 2,15}, { 1, 5, 3,14}, { 1,13, 2, 7}, {-1,13, 3, 6} },
+    { {-1, 1, 6,11}, { 1, 1, 7,10}, { 1, 5, 2,11}, {-1, 5, 3,10}, {-1, 9, 2, 7}, { 1, 9, 3, 6} },
+    { {-1, 4,10,15}, { 1, 4,11,14}, { 1, 8, 6,15}, {-1, 8, 7,14}, {-1,12, 6,11}, { 1,12, 7,10} },
+    { { 1, 0,10,15}, {-1, 0,11,14}, {-1, 8, 2,15}, { 1, 8, 3,14}, { 1,12, 2,11}, {-1,12, 3,10} },
+    { {-1, 0, 6,15}, { 1, 0, 7,14}, { 1, 4, 2,15}, {-1, 4, 3,14}, {-1,12, 2, 7}, { 1,12, 3, 6} },
+    { { 1, 0, 6,11}, {-1, 0, 7,10}, {-1, 4, 2,11}, { 1, 4, 3,10}, { 1, 8, 2, 7}, {-1, 8, 3, 6} },
+    { { 1, 4, 9,15}, {-1, 4,11,13}, {-1, 8, 5,15}, { 1, 8, 7,13}, { 1,12, 5,11}, {-1,12, 7, 9} },
+    { {-1, 0, 9,15}, { 1, 0,11,13}, { 1, 8, 1,15}, {-1, 8, 3,13}, {-1,12, 1,11}, { 1,12, 3, 9} },
+    { { 1, 0, 5,15}, {-1, 0, 7,13}, {-1, 4, 1,15}, { 1, 4, 3,13}, { 1,12, 1, 7}, {-1,12, 3, 5} },
+    { {-1, 0, 5,11}, { 1, 0, 7, 9}, { 1, 4, 1,11}, {-1, 4, 3, 9}, {-1, 8, 1, 7}, { 1, 8, 3, 5} },
+    { {-1, 4, 9,14}, { 1, 4,10,13}, { 1, 8, 5,14}, {-1, 8, 6,13}, {-1,12, 5,10}, { 1,12, 6, 9} },
+    { { 1, 0, 9,14}, {-1, 0,10,13}, {-1, 8, 1,14}, { 1, 8, 2,13}, { 1,12, 1,10}, {-1,12, 2, 9} },
+    { {-1, 0, 5,14}, { 1, 0, 6,13}, { 1, 4, 1,14}, {-1, 4, 2,13}, {-1,12, 1, 6}, { 1,12, 2, 5} },
+    { { 1, 0, 5,10}, {-1, 0, 6, 9}, {-1, 4, 1,10}, { 1, 4, 2, 9}, { 1, 8, 1, 6}, {-1, 8, 2, 5} },
+};
+
 M4 inverse(const M4& a)
 {
-    const float (*m)[4] = a.m;
-    float s0 = m[0][0] * m[1][1] - m[1][0] * m[0][1], s1 = m[0][0] * m[1][2] - m[1][0] * m[0][2];
-    float s2 = m[0][0] * m[1][3] - m[1][0] * m[0][3], s3 = m[0][1] * m[1][2] - m[1][1] * m[0][2];
-    float s4 = m[0][1] * m[1][3] - m[1][1] * m[0][3], s5 = m[0][2] * m[1][3] - m[1][2] * m[0][3];
-    float c5 = m[2][2] * m[3][3] - m[3][2] * m[2][3], c4 = m[2][1] * m[3][3] - m[3][1] * m[2][3];
-    float c3 = m[2][1] * m[3][2] - m[3][1] * m[2][2], c2 = m[2][0] * m[3][3] - m[3][0] * m[2][3];
-    float c1 = m[2][0] * m[3][2] - m[3][0] * m[2][2], c0 = m[2][0] * m[3][1] - m[3][0] * m[2][1];
-    float det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
-    float id = 1.f / det;
+    const float* m = &a.m[0][0];
+    float inv[16];
+    for (int k = 0; k < 16; k++) {
+        float acc = 0.f;
+        for (int t = 0; t < 6; t++) {
+            const signed char* q = kCofactor[k][t];
+            const float prod = m[q[1]] * m[q[2]] * m[q[3]];              // left to right, as written in the reference
+            if (t == 0) acc = q[0] < 0 ? -prod : prod;                    // (-x) * y * z == -(x * y * z) exactly
+            else acc = q[0] < 0 ? acc - prod : acc + prod;
+        }
+        inv[k] = acc;
+    }
+    float det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    det = 1.f / det;
     M4 r;
-    r.m[0][0] = (m[1][1] * c5 - m[1][2] * c4 + m[1][3] * c3) * id;
-    r.m[0][1] = (-m[0][1] * c5 + m[0][2] * c4 - m[0][3] * c3) * id;
-    r.m[0][2] = (m[3][1] * s5 - m[3][2] * s4 + m[3][3] * s3) * id;
-    r.m[0][3] = (-m[2][1] * s5 + m[2][2] * s4 - m[2][3] * s3) * id;
-    r.m[1][0] = (-m[1][0] * c5 + m[1][2] * c2 - m[1][3] * c1) * id;
-    r.m[1][1] = (m[0][0] * c5 - m[0][2] * c2 + m[0][3] * c1) * id;
-    r.m[1][2] = (-m[3][0] * s5 + m[3][2] * s2 - m[3][3] * s1) * id;
-    r.m[1][3] = (m[2][0] * s5 - m[2][2] * s2 + m[2][3] * s1) * id;
-    r.m[2][0] = (m[1][0] * c4 - m[1][1] * c2 + m[1][3] * c0) * id;
-    r.m[2][1] = (-m[0][0] * c4 + m[0][1] * c2 - m[0][3] * c0) * id;
-    r.m[2][2] = (m[3][0] * s4 - m[3][1] * s2 + m[3][3] * s0) * id;
-    r.m[2][3] = (-m[2][0] * s4 + m[2][1] * s2 - m[2][3] * s0) * id;
-    r.m[3][0] = (-m[1][0] * c3 + m[1][1] * c1 - m[1][2] * c0) * id;
-    r.m[3][1] = (m[0][0] * c3 - m[0][1] * c1 + m[0][2] * c0) * id;
-    r.m[3][2] = (-m[3][0] * s3 + m[3][1] * s1 - m[3][2] * s0) * id;
-    r.m[3][3] = (m[2][0] * s3 - m[2][1] * s1 + m[2][2] * s0) * id;
+    float* o = &r.m[0][0];
+    for (int k = 0; k < 16; k++) o[k] = inv[k] * det;
     return r;
 }
+
+// Transform (transform.h:69-123): a matrix and its inverse carried side by side; the product multiplies the
+// inverses in the opposite order instead of inverting the product (transform.cpp:198-203).
+struct T4 { M4 m, inv; };
+T4 t4(const M4& m) { T4 r; r.m = m; r.inv = inverse(m); return r; }
+T4 t4(const M4& m, const M4& inv) { T4 r; r.m = m; r.inv = inv; return r; }
 
 void normalize3(float v[3])
 {
@@ -361,8 +380,22 @@ void cross3(const float a[3], const float b[3], float r[3])
 
 float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
-M4 scale_m(float x, float y, float z) { M4 r = ident(); r.m[0][0] = x; r.m[1][1] = y; r.m[2][2] = z; return r; }
-M4 translate_m(float x, float y, float z) { M4 r = ident(); r.m[0][3] = x; r.m[1][3] = y; r.m[2][3] = z; return r; }
+M4 mul(const M4& a, const M4& b);
+T4 mul(const T4& a, const T4& b) { return t4(mul(a.m, b.m), mul(b.inv, a.inv)); }
+T4 scale_t(float x, float y, float z)        // scale(), transform.cpp:276-288
+{
+    M4 m = ident(), i = ident();
+    m.m[0][0] = x; m.m[1][1] = y; m.m[2][2] = z;
+    i.m[0][0] = 1.0f / x; i.m[1][1] = 1.0f / y; i.m[2][2] = 1.0f / z;
+    return t4(m, i);
+}
+T4 translate_t(float x, float y, float z)    // translate(), transform.cpp:262-274
+{
+    M4 m = ident(), i = ident();
+    m.m[0][3] = x; m.m[1][3] = y; m.m[2][3] = z;
+    i.m[0][3] = -x; i.m[1][3] = -y; i.m[2][3] = -z;
+    return t4(m, i);
+}
 
 // Transform::tPoint, transform.h:126-140 (+ Vector3 operator/ returning INF on |w| <= EPS, vector.cpp:35-39)
 void t_point(const float m[16], const float p[3], float out[3])
@@ -379,7 +412,8 @@ void t_point(const float m[16], const float p[3], float out[3])
 
 }  // namespace
 
-// Camera::setup, camera.cpp:3-29 (lookAt transform.cpp:353-370, perspective :379-387).
+// Camera::setup, camera.cpp:3-29 (lookAt transform.cpp:353-370, perspective :379-387), operation for operation:
+// the matrices are bit-identical to the reference's (tests/test_host.py::test_camera_setup_bit_identical_to_reference).
 void camera_setup(const float pos_in[3], const float fwd_in[3], const float up_in[3], float xres, float yres,
                   float fov, wrt_camera* out)
 {
@@ -389,38 +423,40 @@ void camera_setup(const float pos_in[3], const float fwd_in[3], const float up_i
     float up[3] = { up_in[0], up_in[1], up_in[2] };
     normalize3(fwd); normalize3(up);
 
-    // lookAt(pos, pos + forward, up): rows are (up x -dir), (that x dir), -dir
+    // lookAt(pos, pos + forward, up): _dir = look - pos (normalised), _up = up x (-_dir) (normalised), _left = _up x _dir;
+    // rows (_up, -_up.pos), (_left, -_left.pos), (-_dir, +_dir.pos... as -(-_dir.pos))
     float look[3] = { pos[0] + fwd[0], pos[1] + fwd[1], pos[2] + fwd[2] };
     float dir[3] = { look[0] - pos[0], look[1] - pos[1], look[2] - pos[2] };
     normalize3(dir);
     float ndir[3] = { -dir[0], -dir[1], -dir[2] };
     float ux[3]; cross3(up, ndir, ux); normalize3(ux);
     float lf[3]; cross3(ux, dir, lf);
-    M4 w2c = ident();
-    float px = dot3(ux, pos), py = dot3(lf, pos), pz = dot3(ndir, pos);
-    for (int a = 0; a < 3; a++) { w2c.m[0][a] = ux[a]; w2c.m[1][a] = lf[a]; w2c.m[2][a] = ndir[a]; }
-    w2c.m[0][3] = -px; w2c.m[1][3] = -py; w2c.m[2][3] = -pz;
+    M4 w2c_m = ident();
+    const float px = dot3(ux, pos), py = dot3(lf, pos), pz = dot3(ndir, pos);
+    for (int a = 0; a < 3; a++) { w2c_m.m[0][a] = ux[a]; w2c_m.m[1][a] = lf[a]; w2c_m.m[2][a] = ndir[a]; }
+    w2c_m.m[0][3] = -px; w2c_m.m[1][3] = -py; w2c_m.m[2][3] = -pz;
+    const T4 w2c = t4(w2c_m);
 
-    // perspective(fov, 0.1, 10000) = scale(1/tan, 1/tan, 1) * persp
+    // perspective(fov, 0.1, 10000) = scale(1/tan, 1/tan, 1) * Transform(persp)
     const float zn = 0.1f, zf = 10000.f;
     M4 persp = ident();
     persp.m[1][1] = -1.f;
     persp.m[2][2] = (zn + zf) / (zf - zn); persp.m[2][3] = 2 * zf * zn / (zf - zn);
     persp.m[3][2] = -1.f; persp.m[3][3] = 0.f;
-    float inv_tan = 1.0f / tanf(fov / 360.0f * pi);
-    M4 proj = mul(scale_m(inv_tan, inv_tan, 1.f), persp);
+    const float inv_tan = 1.0f / tanf(fov / 360.0f * pi);
+    const T4 proj = mul(scale_t(inv_tan, inv_tan, 1.f), t4(persp));
 
-    M4 w2ns = mul(proj, w2c);
-    M4 ns2w = mul(inverse(w2c), inverse(proj));  // Transform product keeps mInv = t2.mInv * t1.mInv
-    M4 w2r = mul(mul(scale_m(xres * 0.5f, yres * 0.5f, 0.f), translate_m(1.f, 1.f, 0.f)), w2ns);
-    M4 r2w = mul(mul(ns2w, translate_m(-1.f, -1.f, 0.f)), scale_m(2.0f / xres, 2.0f / yres, 0.f));
+    const T4 w2ns = mul(proj, w2c);
+    const T4 ns2w = t4(w2ns.inv, w2ns.m);                                 // inverse(Transform)
+    const T4 w2r = mul(mul(scale_t(xres * 0.5f, yres * 0.5f, 0.f), translate_t(1.0f, 1.0f, 0.0f)), w2ns);
+    const T4 r2w = mul(mul(ns2w, translate_t(-1.0f, -1.0f, 0.0f)), scale_t(2.0f / xres, 2.0f / yres, 0.f));
 
     for (int a = 0; a < 3; a++) { out->pos[a] = pos[a]; out->forward[a] = fwd[a]; }
     out->x_res = xres; out->y_res = yres;
-    float tan_half = tanf(fov * pi / 360.0f);
+    const float tan_half = tanf(fov * pi / 360.0f);
     out->image_plane_dist = xres / (2.0f * tan_half);
-    memcpy(out->raster_to_world, r2w.m, sizeof(float) * 16);
-    memcpy(out->world_to_raster, w2r.m, sizeof(float) * 16);
+    memcpy(out->raster_to_world, r2w.m.m, sizeof(float) * 16);
+    memcpy(out->world_to_raster, w2r.m.m, sizeof(float) * 16);
 }
 
 void make_ray(const float* q, wrt_ray* r)  // Ray(origin, dir), ray.h:14-16 + Vector3::normalize vector.h:62-66
