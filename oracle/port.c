@@ -217,6 +217,36 @@ void port_occluded(const port_scene* s, const float* q9, long long n, uint8_t* o
     }
 }
 
+/* Scene::shadowRayTest(ray, p), scene.cpp:55-69: the ray is taken as given (no re-normalisation); 1.0 = visible. */
+void port_shadow_test(const port_scene* s, const float* rays8, const float* target3, long long n, float* visible)
+{
+    long long i;
+    for (i = 0; i < n; i++) {
+        ray_t ray; inter_t in;
+        int g, eq;
+        float hp[3];
+        const float* p = target3 + 3 * i;
+        load_ray(rays8 + 8 * i, &ray);
+        g = traverse(s, &ray, NULL);
+        if (g < 0) { visible[i] = 1.0f; continue; }
+        prim_hit(s, g, &ray, &in, NULL);
+        hp[0] = ray.o[0] + ray.d[0] * in.t; hp[1] = ray.o[1] + ray.d[1] * in.t; hp[2] = ray.o[2] + ray.d[2] * in.t;
+        eq = cmpf(hp[0] - p[0]) == 0 && cmpf(hp[1] - p[1]) == 0 && cmpf(hp[2] - p[2]) == 0;
+        visible[i] = eq ? 1.0f : 0.0f;
+    }
+}
+
+/* bool Scene::intersect(ray), scene.cpp:45-53: a full closest-hit traversal, only hit / no hit is returned. */
+void port_intersect_any(const port_scene* s, const float* rays8, long long n, uint8_t* hit)
+{
+    long long i;
+    for (i = 0; i < n; i++) {
+        ray_t ray;
+        load_ray(rays8 + 8 * i, &ray);
+        hit[i] = traverse(s, &ray, NULL) >= 0 ? 1 : 0;
+    }
+}
+
 int port_triangle_hit(const float* tri9, const float* ray8, float* t)
 {
     ray_t ray; inter_t in; int h;

@@ -22,6 +22,8 @@ void port_intersect(const port_scene* s, const float* rays8, long long n, int32_
                     float* p3, float* n3, int32_t* inside, int32_t* matid, unsigned long long* counters);
 void port_occluded(const port_scene* s, const float* p1_dir_p2, long long n, uint8_t* occluded);
 void port_make_rays(const float* origin_dir6, long long n, float* rays8);
+void port_shadow_test(const port_scene* s, const float* rays8, const float* target3, long long n, float* visible);
+void port_intersect_any(const port_scene* s, const float* rays8, long long n, uint8_t* hit);
 int port_triangle_hit(const float* tri9, const float* ray8, float* t);
 int port_sphere_hit(const float* cr4, const float* ray8, float* t, int* inside);
 int port_aabb_hit(const float* box6, const float* ray8, float* t1, float* t2);

@@ -75,6 +75,20 @@ class PortScene:
         return occ
 
 
+    def shadow_test(self, rays8, target3):
+        r = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)
+        p = np.ascontiguousarray(target3, np.float32).reshape(-1, 3)
+        vis = np.zeros(len(r), np.float32)
+        lib().port_shadow_test(C.byref(self.s), r.ctypes.data_as(_f32p), p.ctypes.data_as(_f32p), C.c_longlong(len(r)), vis.ctypes.data_as(_f32p))
+        return vis
+
+    def intersect_any(self, rays8):
+        r = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)
+        hit = np.zeros(len(r), np.uint8)
+        lib().port_intersect_any(C.byref(self.s), r.ctypes.data_as(_f32p), C.c_longlong(len(r)), hit.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return hit
+
+
 def make_rays(od6):
     od = np.ascontiguousarray(od6, np.float32).reshape(-1, 6)
     out = np.zeros((len(od), 8), np.float32)

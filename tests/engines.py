@@ -14,6 +14,10 @@ class PortEngine:
         return self.port.intersect(rays, full=full)
     def occluded(self, q9):
         return self.port.occluded(q9)
+    def shadow_test(self, rays, p3):
+        return self.port.shadow_test(rays, p3)
+    def intersect_any(self, rays):
+        return self.port.intersect_any(rays)
 
 
 class RefEngine:
@@ -24,6 +28,10 @@ class RefEngine:
         return self.ref.intersect(rays, full=full)
     def occluded(self, q9):
         return self.ref.occluded(q9)
+    def shadow_test(self, rays, p3):
+        return self.ref.shadow_test(rays, p3)
+    def intersect_any(self, rays):
+        return self.ref.intersect_any(rays)
 
 
 class HostSimEngine:
@@ -49,6 +57,10 @@ class CudaEngine:
         return self.scene.intersect(rays, full=full)
     def occluded(self, q9):
         return self.scene.occluded(q9)
+    def shadow_test(self, rays, p3):
+        return self.scene.shadowRayTest(rays, p3)
+    def intersect_any(self, rays):
+        return self.scene.intersect_any(rays)
 
 
 def check_against_golden(wrt, engine, sc, z):
@@ -105,3 +117,82 @@ def adversarial_rays(sc, n=20000, seed=3):
     d = rng.normal(size=(m, 3)).astype(np.float32)
     out.extend(np.concatenate([o, d], 1))
     return np.asarray(out, np.float32)
+
+
+def grazing_rays(sc, n=20000, seed=5, top_fraction=0.02):
+    """rays that graze triangles at angles from 0 to 1e-3 rad (0.057 deg) — the regime where the computed
+    t / barycentrics of Triangle::hit carry the largest float error and a conservative-bounds test is most at risk.  Targets are
+    the largest triangles of the scene (walls, floors, light quads: half of the rays) and random ones; the ray passes through
+    a point on or just outside the triangle (barycentric slack around the reference's -EPS acceptance edge) in a direction lying in
+    the triangle's plane, tilted out of it by +-theta."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tri = sc.data[sc.kind == 0].astype(np.float64)
+    p0, p1, p2 = tri[:, 0:3], tri[:, 3:6], tri[:, 6:9]
+    nrm = np.cross(p1 - p0, p2 - p0)
+    area = 0.5 * np.linalg.norm(nrm, axis=1)
+    ok = area > 0
+    big = np.argsort(-area)[: max(2, int(len(tri) * top_fraction))]
+    pick = np.where(rng.random(n) < 0.5, big[rng.integers(0, len(big), n)], rng.integers(0, len(tri), n))
+    pick = pick[ok[pick]]
+    n = len(pick)
+    a, b, c = p0[pick], p1[pick], p2[pick]
+    nn = nrm[pick] / np.linalg.norm(nrm[pick], axis=1, keepdims=True)
+    # point on / around the triangle: barycentrics in [-3e-3, 1 + 3e-3], a third of them hugging an edge
+    u = rng.random((n, 2))
+    flip = u.sum(1) > 1; u[flip] = 1 - u[flip]
+    edge = rng.random(n) < 0.33
+    u[edge, 0] = rng.choice(np.array([-2e-3, -1e-3, -5e-4, 0.0, 5e-4, 1e-3]), edge.sum())
+    P = a + (b - a) * u[:, :1] + (c - a) * u[:, 1:]
+    # in-plane direction, tilted by theta out of the plane
+    e = (b - a) / np.linalg.norm(b - a, axis=1, keepdims=True)
+    f = np.cross(nn, e)
+    phi = rng.random(n) * 2 * np.pi
+    d_in = e * np.cos(phi)[:, None] + f * np.sin(phi)[:, None]
+    theta = rng.choice(np.array([0.0, 1e-7, 1e-6, 1e-5, 5e-5, 1e-4, 1.7e-4, 5e-4, 1e-3]), n) * rng.choice(np.array([-1.0, 1.0]), n)
+    d = d_in * np.cos(theta)[:, None] + nn * np.sin(theta)[:, None]
+    ext = np.linalg.norm(tri.reshape(-1, 3).max(0) - tri.reshape(-1, 3).min(0))
+    L = ext * (0.05 + 2.0 * rng.random(n))
+    o = P - d * L[:, None]
+    return np.concatenate([o, d], axis=1).astype(np.float32)
+
+
+def far_scene(sc, scale=1000.0, offset=(5000.0, -3000.0, 2000.0)):
+    """The same scene blown up and moved away from the origin (coordinates in the thousands: float spacing 1e-3 .. 5e-4,
+    i.e. of the order of the reference's EPS) — 'huge-coordinate scenes' of VERDICT r1 item 1e."""
+    import copy
+    s2 = copy.copy(sc)
+    data = sc.data.astype(np.float64).copy()
+    off = np.asarray(offset, np.float64)
+    tri = sc.kind == 0
+    data[tri] = (data[tri].reshape(-1, 3, 3) * scale + off).reshape(-1, 9)
+    data[~tri, 0:3] = data[~tri, 0:3] * scale + off
+    data[~tri, 3] *= scale
+    s2.data = data.astype(np.float32)
+    lights = sc.lights.astype(np.float64).copy()
+    lights[:, 0:9] = (lights[:, 0:9].reshape(-1, 3, 3) * scale + off).reshape(-1, 9)
+    s2.lights = lights.astype(np.float32)
+    cam = sc.cam12.astype(np.float64).copy(); cam[0:3] = cam[0:3] * scale + off
+    s2.cam12 = cam.astype(np.float32)
+    s2.name = sc.name + "_far"
+    return s2
+
+
+def shadow_test_queries(port, rays, seed=9):
+    """Scene::shadowRayTest(ray, p) inputs with targets ON and OFF the surfaces: p = the ray's own closest hit point moved by
+    0, +-0.5, +-0.9, +-1.1, +-1.5, +-4 EPS along one axis (around the component-wise tolerance of Vector3 ==), points half-way
+    to the hit, points beyond it, and random points for rays that miss everything."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    prim, t, p, n, ins, mat = port.intersect(rays, full=True)
+    tgt = p.copy()
+    k = np.arange(len(rays))
+    eps = np.float32(1e-3)
+    mult = np.array([0.0, 0.5, -0.5, 0.9, -0.9, 1.1, -1.1, 1.5, -1.5, 4.0, -4.0], np.float32)[k % 11]
+    ax = (k // 11) % 3
+    tgt[k, ax] += mult * eps
+    half = (k % 17) == 5
+    tgt[half] = (rays[half, 0:3] + rays[half, 3:6] * (t[half] * np.float32(0.5))[:, None])
+    beyond = (k % 17) == 9
+    tgt[beyond] = (rays[beyond, 0:3] + rays[beyond, 3:6] * (t[beyond] * np.float32(1.5))[:, None])
+    miss = prim < 0
+    tgt[miss] = rng.normal(size=(miss.sum(), 3)).astype(np.float32)
+    return tgt.astype(np.float32)

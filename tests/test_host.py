@@ -248,3 +248,42 @@ def test_layout_rejects_what_the_kernels_cannot_index(wrt):
     chain.update(axis=axis, split=split, left=left.astype(np.int32), right=right.astype(np.int32), first_ref=first, nref=nref)
     with pytest.raises(RuntimeError, match="too deep"):
         build(tree=chain)
+
+
+def test_kd_build_matches_reference_at_headline_scale(wrt, have_ref):
+    """VERDICT r1 'weak' 4: the tree the headline benchmark (C3, 1 002 528 triangles + 2 light triangles) traverses is the
+    reference's own tree, node for node and reference for reference — KDtreeAccel::init + buildTree (KDtreeAccel.cpp:12-307)
+    run by the compiled reference against host/kd_build.cpp, live (about 10 s)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.synthetic_torus_scene(n=708, width=1920, height=1080)
+    assert sc.n_prims == 1002530
+    hs = util.host_scene(wrt, sc)
+    ref = util.ref_scene(sc)
+    a, b = hs.arrays()["tree"], ref.tree()
+    assert len(a["axis"]) == len(b["axis"]) > 300000 and len(a["refs"]) == len(b["refs"]) > 1500000
+    for k in ("axis", "left", "right", "nref", "refs"):
+        assert np.array_equal(a[k], b[k]), k
+    inner = b["axis"] >= 0
+    assert np.array_equal(util.bits(a["split"][inner]), util.bits(b["split"][inner]))
+    assert np.array_equal(a["first_ref"][~inner], b["first_ref"][~inner])
+    assert np.array_equal(util.bits(a["root_box"]), util.bits(b["box"][0]))
+
+
+def test_camera_setup_bit_identical_to_reference(wrt, have_ref):
+    """Camera::setup (camera.cpp:3-29, lookAt / perspective / inverse of transform.cpp) restated operation for operation:
+    rasterToWorld, worldToRaster and imagePlaneDist are bit-identical — incl. torus.scene's camera, whose coordinates are in
+    the thousands (an ulp in the matrix moves primary rays there)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    cams = [scenes.load_fixture(n)[0].cam12 for n in FIXTURES] + [scenes.synthetic_torus_scene(n=8, width=1920, height=1080).cam12,
+            np.array([3, -2, 1.5, -0.3, 0.9, -0.1, 0.1, 0.2, 0.97, 640, 480, 63.5], np.float32)]
+    sc = scenes.small_mixed_scene()
+    for c in cams:
+        sc.cam12 = np.asarray(c, np.float32)
+        want = util.ref_scene(sc).camera()
+        cam = wrt.camera_setup(c[0:3], c[3:6], c[6:9], c[9], c[10], c[11])
+        assert np.array_equal(util.bits(np.array(cam.raster_to_world[:], np.float32)), util.bits(want[13:29]))
+        assert np.array_equal(util.bits(np.array(cam.world_to_raster[:], np.float32)), util.bits(want[29:45]))
+        assert np.float32(cam.image_plane_dist) == want[12]
+        assert np.array_equal(util.bits(np.array(list(cam.pos) + list(cam.forward), np.float32)), util.bits(want[0:6]))

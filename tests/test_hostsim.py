@@ -236,3 +236,30 @@ def test_warpsim_nan_interval_and_tiny_batches(wrt):
         got = ws.trace_closest(rays[:m], True, 3)
         assert np.array_equal(got[0], want[0][:m]) and np.array_equal(util.bits(got[1]), util.bits(want[1][:m])), m
     assert len(ws.trace_closest(rays[:0], True, 3)[0]) == 0
+
+
+@pytest.mark.parametrize("name", ["synthetic", "torus", "synthetic_far"])
+def test_grazing_rays_on_the_host_build(wrt, name):
+    """CPU twin of test_gpu_traversal.py::test_grazing_rays_exact_is_exact_and_pruned_differs_only_in_plane: EXACT == oracle on rays
+    in triangle planes; every PRUNED disagreement is an in-plane event (|cos| <= 2e-5 to a winner's normal)."""
+    import engines
+    base = scenes.synthetic_torus_scene(n=48, width=64, height=64, n_spheres=300) if name.startswith("synthetic") else scenes.load_fixture("torus")[0]
+    sc = engines.far_scene(base) if name.endswith("_far") else base
+    rays = wrt.make_rays(engines.grazing_rays(sc, 60000, seed=31))
+    port = engines.PortEngine(wrt, sc)
+    want = port.intersect(rays)
+    ex = engines.HostSimEngine(wrt, sc, False).intersect(rays)
+    assert np.array_equal(ex[0], want[0]) and np.array_equal(util.bits(ex[1]), util.bits(want[1]))
+    pr = engines.HostSimEngine(wrt, sc, True).intersect(rays)
+    bad = np.nonzero(pr[0] != want[0])[0]
+    assert 0 < len(bad) <= 0.005 * len(rays)          # the generator does reach the class (if it stops doing so, it has lost its point)
+    tri = sc.data.astype(np.float64)
+    worst = 0.0
+    for i in bad:
+        cs = []
+        for p in (want[0][i], pr[0][i]):
+            if p >= 0 and sc.kind[p] == 0:
+                T = tri[p]; n = np.cross(T[3:6] - T[0:3], T[6:9] - T[0:3]); n /= np.linalg.norm(n)
+                cs.append(abs(float(n @ rays[i, 3:6].astype(np.float64))))
+        worst = max(worst, min(cs))
+    assert worst <= 2e-5, worst

@@ -78,3 +78,20 @@ def test_primitive_kats(have_ref):
         h2 = P.port_aabb_hit(box.ctypes.data_as(f32p), ray.ctypes.data_as(f32p), C.byref(b1), C.byref(b2))
         assert h1 == h2
         if h1: assert a1.value == b1.value and a2.value == b2.value
+
+
+@pytest.mark.parametrize("name", ["torus", "small_mixed"])
+def test_port_shadow_any_and_grazing_match_reference(wrt, have_ref, name):
+    """Pins the round-2 additions of the port: Scene::shadowRayTest with off-surface targets, bool Scene::intersect, and the
+    grazing-ray class (rays in triangle planes, where Triangle::hit divides rounding noise by rounding noise): bit equality."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.load_fixture(name)[0] if name != "small_mixed" else scenes.small_mixed_scene()
+    port = engines.PortEngine(wrt, sc); ref = engines.RefEngine(wrt, sc)
+    rays = wrt.make_rays(np.concatenate([engines.adversarial_rays(sc, 8000, seed=21), engines.grazing_rays(sc, 12000, seed=22, top_fraction=1.0)]))
+    a, b = port.intersect(rays), ref.intersect(rays)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(util.bits(a[1]), util.bits(b[1]))
+    tgt = engines.shadow_test_queries(port, rays)
+    vis = port.shadow_test(rays, tgt)
+    assert np.array_equal(vis, ref.shadow_test(rays, tgt)) and 0.2 < vis.mean() < 0.9
+    assert np.array_equal(port.intersect_any(rays), ref.intersect_any(rays))

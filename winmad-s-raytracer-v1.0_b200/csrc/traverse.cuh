@@ -113,11 +113,15 @@ WRT_HD bool sphere_t(float cx, float cy, float cz, float radius, const float lo[
 // kd_traverse() below runs them in a plain loop; the persistent kernels (trace_persistent.cuh) run the
 // SAME steps but let idle lanes of a warp pick up new rays in between.  Either way every ray performs
 // the same arithmetic in the same order.
-// A ray for which a slab product can be NaN: zero / infinite / NaN direction components (invDir infinite, zero or NaN)
-// or a non-finite origin.  Axis-parallel rays are the common case; they keep the guarded test.
+// A ray for which a kd interval can be NaN or infinite: zero / tiny / infinite / NaN direction components (invDir infinite,
+// huge, zero or NaN) or a non-finite origin.  Axis-parallel rays are the common case.  PRUNED traversal does not prune
+// for such rays (box_prunable): with t = (split - o) * (+-inf) the reference's intervals become NaN / inf, its stack is
+// no longer ordered by tmin, and the rule "stop the WHOLE traversal at the first popped entry with ray.tmax < tmin"
+// (KDtreeAccel.cpp:323) can fire on an entry that lives INSIDE a sub-tree — skipping that sub-tree would let the traversal
+// run on and find hits the reference never sees (found by the grazing-ray generator, tests/engines.py).
 WRT_HD bool ray_is_degenerate(const RayIn& r, float ix, float iy, float iz)
 {
-    const float big = 3.0e38f;
+    const float big = 1.0e30f;     // |invDir| below this: (split - o) * invDir cannot overflow for coordinates < 1e7 (INF)
     const bool inv_ok = fabsf(ix) < big && fabsf(iy) < big && fabsf(iz) < big && ix != 0.f && iy != 0.f && iz != 0.f;
     const bool org_ok = fabsf(r.ox) < big && fabsf(r.oy) < big && fabsf(r.oz) < big;
     return !(inv_ok && org_ok);
@@ -143,31 +147,8 @@ WRT_HD bool trav_begin(const DevSceneView& sc, const RayIn& r, Trav& T)
     return true;
 }
 
-// Entry AND exit distance of the ray through a conservative box (NaN slabs are ignored, i.e. never prune).
-WRT_HD void box_interval(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayIn& r,
-                         float ix, float iy, float iz, float& entry, float& exit_)
-{
-    float t0 = (lox - r.ox) * ix, t1 = (hix - r.ox) * ix;
-    bool nn = (t0 != t0 || t1 != t1);
-    const float ex = nn ? -HUGE_VALF : fminf(t0, t1), xx = nn ? HUGE_VALF : fmaxf(t0, t1);
-    t0 = (loy - r.oy) * iy; t1 = (hiy - r.oy) * iy;
-    nn = (t0 != t0 || t1 != t1);
-    const float ey = nn ? -HUGE_VALF : fminf(t0, t1), xy = nn ? HUGE_VALF : fmaxf(t0, t1);
-    t0 = (loz - r.oz) * iz; t1 = (hiz - r.oz) * iz;
-    nn = (t0 != t0 || t1 != t1);
-    const float ez = nn ? -HUGE_VALF : fminf(t0, t1), xz = nn ? HUGE_VALF : fmaxf(t0, t1);
-    entry = fmaxf(ex, fmaxf(ey, ez));
-    exit_ = fminf(xx, fminf(xy, xz));
-}
-
-WRT_HD void bound_interval(const float4 a, const float4 b, const RayIn& r, float ix, float iy, float iz, float& entry, float& exit_)
-{
-    box_interval(a.z, a.w, b.x, b.y, b.z, b.w, r, ix, iy, iz, entry, exit_);
-}
-
-// Same interval for a "regular" ray: finite origin, finite non-zero invDir (ray_is_degenerate() == false).  No slab can
-// be NaN then ((finite or +-inf bound - finite) * finite non-zero), so the NaN guards — a third of the instructions of
-// the box test — are dropped; the values computed are identical to box_interval's.
+// Entry and exit distance of a "regular" ray (finite origin, finite non-zero invDir: ray_is_degenerate() == false) through a
+// conservative box.  No slab can be NaN then ((finite or +-inf bound - finite) * finite non-zero), so no NaN guards are needed.
 WRT_HD void box_interval_regular(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayIn& r,
                                  float ix, float iy, float iz, float& entry, float& exit_)
 {
@@ -183,9 +164,9 @@ WRT_HD void box_interval_regular(float lox, float loy, float loz, float hix, flo
 WRT_HD bool box_prunable(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayIn& r,
                          float ix, float iy, float iz, int res, float best, bool degenerate)
 {
+    if (degenerate) return false;         // see ray_is_degenerate(): such rays take the reference's full traversal
     float en, ex;
-    if (degenerate) box_interval(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz, en, ex);
-    else box_interval_regular(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz, en, ex);
+    box_interval_regular(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz, en, ex);
     if (res >= 0 && en > best * WRT_PRUNE_REL) return true;
     const float m = 1e-4f * (fabsf(en) + fabsf(ex)) + 1e-4f;
     return (en > ex + m) || (ex < -m);
