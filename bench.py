@@ -12,8 +12,10 @@ Printed JSON (one line, rank 0): value = whole-job Mrays/s with everything resid
 events, max over ranks); e2e = the same through the host-buffer C-ABI call (film copied back to pinned
 host memory every step); roofline = the closest-hit (extend) kernel's algorithmic GB/s against the
 measured HBM peak; cpu_baseline = the reference's own renderer timed on this box's host cores on a
-bounded sample.  N > 1 (torchrun): every rank renders the full frame at 64 spp with its own RNG stream
-(weak scaling), films are summed with one NCCL reduce inside the timed region.
+bounded sample.  N > 1 (torchrun): STRONG scaling by default — the workload's samples per pixel (iterations for BDPT)
+are dealt round-robin to the ranks (same stratification grid, same RNG keys as the 1-GPU render), films
+are summed with one NCCL reduce inside the timed region (its device time is reported as reduce_ms), and rank 0 checks
+the N-GPU film against the 1-GPU film (T4: max relative difference).  --scaling weak: every rank renders the full spp.
 """
 import argparse
 import json
@@ -31,6 +33,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import numpy as np  # noqa: E402
 
 WORKLOADS = {
+    "c1": dict(desc="C1 (BASELINE configs[0]): torus.scene as shipped (13,486 triangles, glass + diffuse), 512x512 PT, depth 7, 1 spp",
+               integrator="pt", width=512, height=512, spp=1, depth=7, fixture="torus"),
     "c3": dict(desc="C3: synthetic 1,002,528-triangle displaced torus + 2-triangle area light, 1920x1080 PT, depth 5, 64 spp",
                integrator="pt", width=1920, height=1080, spp=64, depth=5, n=708),
     "torus": dict(desc="C1-class: torus.scene (13,486 triangles, glass + diffuse), 512x512 PT, depth 7, 256 spp",
@@ -53,6 +57,17 @@ WORKLOADS = {
 # one 33 554 432-ray launch, 22.52 GB + 4.88 GB).
 NCU_DRAM_BYTES_PER_RAY = {"c3": (4.749402e9 + 1.546372e9) / 33554432.0, "c5": (22.523734e9 + 4.877666e9) / 33554432.0}
 NCU_SOURCE = {"c3": "profiles/r1_final_launches_and_ncu.md", "c5": "profiles/r1_ncu_extend_c5.md"}
+
+
+def ncu_metrics(workload):
+    """Counters of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/ncu_metrics.json,
+    written by tools/ncu_summary.py from the .ncu-rep of the same command): DRAM bytes per ray, issue-slot utilisation,
+    threads per instruction.  They explain the live number; they are never measured under the profiler in this run."""
+    try:
+        m = json.load(open(os.path.join(ROOT, "profiles", "ncu_metrics.json")))
+        return m.get(workload)
+    except Exception:
+        return None
 
 
 def make_scene(w):
@@ -199,8 +214,8 @@ def reference_workload(w):
     elif w["integrator"] == "whitted":
         w["row_stride"] = 1              # whole frame at 1 spp per process
     else:
-        w["width"] = w["height"] = 256   # BDPT must render whole (square) frames: 1 iteration at 256^2
-        w["row_stride"] = 1
+        w["width"] = w["height"] = 512   # BidirPathTracing::runIteration renders whole square frames (all W*H light paths, then all
+        w["row_stride"] = 1              # camera paths): 1 iteration of the same scene at 512^2 (same path-length mix) instead of 1440^2
     return w
 
 
@@ -214,9 +229,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("WRT_BENCH_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (PT) / iterations (BDPT)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default): every GPU renders the workload's spp; strong: the spp (iterations) are sharded over the GPUs "
-                         "(samples k = rank, rank + N, ... of the same stratification grid, SURVEY.md 8e)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="strong (default at N > 1): the spp (iterations) are sharded over the GPUs (samples k = rank, rank + N, ... of the "
+                         "same stratification grid, SURVEY.md 8e); weak: every GPU renders the workload's spp")
     args = ap.parse_args()
 
     w = dict(WORKLOADS[args.workload])
@@ -224,6 +239,9 @@ def main():
         w["iterations" if w["integrator"] == "bdpt" else "spp"] = args.spp
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.scaling is None:
+        n_units = w["iterations"] if w["integrator"] == "bdpt" else w["spp"]
+        args.scaling = "strong" if n_units >= world else "weak"     # (C1 has 1 spp: it cannot be sharded)
     metric, unit = "path-tracing ray throughput (closest-hit + shadow rays)", "Mrays/s"
     if w["integrator"] == "bdpt":
         metric = "bidirectional path-tracing ray throughput (closest-hit + connection rays)"
@@ -330,19 +348,22 @@ def main():
 
     # reference-semantics work per ray of THIS ray mix (1 spp / 1 iteration counting render): B_ray
     b_ray, visits, b_ray_k, visits_k = None, None, None, None
-    if rank == 0 and w["integrator"] == "pt":
-        scene.set_counting(True); scene.reset_stats()
-        scene.render_pt(cam, W.PtParams(w["width"], w["height"], 1, w["depth"], 7, 0, 1, 0.0), host_film)
-        s = scene.stats(); scene.set_counting(False)
-        nr = float(s.closest_rays + s.shadow_rays)
-        visits = {"inner": s.inner_visits / nr, "leaf": s.leaf_visits / nr, "tri": s.tri_tests / nr, "sphere": s.sphere_tests / nr}
+    if rank == 0:
+        def count_render(mode):
+            scene.set_counting(mode); scene.reset_stats()
+            if w["integrator"] == "bdpt":
+                scene.render_bdpt(cam, W.BdptParams(w["width"], w["height"], 1, 0, 10, 3, 7, 0, 1, 0.0, 0), host_film)
+            elif w["integrator"] == "whitted":
+                scene.render_whitted(cam, W.PtParams(w["width"], w["height"], 1, w["depth"], 7, 0, 1, 0.0), host_film)
+            else:
+                scene.render_pt(cam, W.PtParams(w["width"], w["height"], 1, w["depth"], 7, 0, 1, 0.0), host_film)
+            s_ = scene.stats(); scene.set_counting(False)
+            nr = float(s_.closest_rays + s_.shadow_rays)
+            return {"inner": s_.inner_visits / nr, "leaf": s_.leaf_visits / nr, "tri": s_.tri_tests / nr, "sphere": s_.sphere_tests / nr}
+        visits = count_render(True)
         b_ray = 40 + 8 * visits["inner"] + 8 * visits["leaf"] + 40 * visits["tri"] + 20 * visits["sphere"]
         # the same accounting for the PRUNED traversal the timed kernels run (their own work, 32-byte nodes, 48-byte records)
-        scene.set_counting(2); scene.reset_stats()
-        scene.render_pt(cam, W.PtParams(w["width"], w["height"], 1, w["depth"], 7, 0, 1, 0.0), host_film)
-        s = scene.stats(); scene.set_counting(False)
-        nr = float(s.closest_rays + s.shadow_rays)
-        visits_k = {"inner": s.inner_visits / nr, "leaf": s.leaf_visits / nr, "tri": s.tri_tests / nr, "sphere": s.sphere_tests / nr}
+        visits_k = count_render(2)
         b_ray_k = 40 + 32 * (visits_k["inner"] + visits_k["leaf"]) + 48 * (visits_k["tri"] + visits_k["sphere"])
 
     def barrier():
@@ -350,37 +371,72 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    red0, red1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reduce_ms = 0.0
+
+    def reduce_film(timed):
+        nonlocal reduce_ms
+        if dist is None:
+            return
+        if timed:
+            red0.record()
+        dist.reduce(film, 0)
+        if timed:
+            red1.record(); red1.synchronize(); reduce_ms += red0.elapsed_time(red1)
+
     for _ in range(max(args.warmup, 3)):
         render_dev(film)
-        if dist is not None:
-            dist.reduce(film, 0)
+        reduce_film(False)
     barrier()
     scene.reset_stats()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ext_ms = ext_rays = ext_launches = 0.0
+    ext_ms = ext_rays = ext_launches = shade_ms = shadow_ms = 0.0
     barrier()
     e0.record()
     for _ in range(args.steps):
         render_dev(film)
-        if dist is not None:
-            dist.reduce(film, 0)
+        reduce_film(True)
         st = scene.stats()
         ext_ms += st.extend_ms; ext_rays += st.extend_rays; ext_launches += st.extend_launches
+        shade_ms += st.shade_ms; shadow_ms += st.shadow_ms
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
     st = scene.stats()
     rays = float(st.closest_rays + st.shadow_rays)
+    closest_rays, shadow_rays = float(st.closest_rays), float(st.shadow_rays)
     launches = int(st.kernel_launches)
     mean_radiance = float(torch.nanmean(film).item()) if rank == 0 else 0.0   # Whitted films hold the reference's NaN pixels
     if dist is not None:
-        tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
+        tt = torch.tensor([ms, reduce_ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms, reduce_ms = float(tt[0].item()), float(tt[1].item())
         rr = torch.tensor([rays, float(launches)], dtype=torch.float64, device="cuda"); dist.all_reduce(rr)
         rays, launches = float(rr[0].item()), int(rr[1].item())
+
+    # T4: the N-GPU film (sum of the rank films, as just reduced onto rank 0) against the 1-GPU film of the same
+    # spp, seed and stratification grid.  RNG keys depend on (pixel, global sample index) only, so every path is the same;
+    # the films differ by float summation order.
+    t4 = None
+    if dist is not None and strong and rank == 0:
+        sharded = film.clone()
+        one = torch.zeros_like(film)
+        if w["integrator"] == "bdpt":
+            scene.render_bdpt_dev(cam, W.BdptParams(w["width"], w["height"], w["iterations"], 0, 10, 3, 1000, 0, 1, 0.0, 0), one.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream)
+        else:
+            fn = scene.render_whitted_dev if w["integrator"] == "whitted" else scene.render_pt_dev
+            fn(cam, W.PtParams(w["width"], w["height"], w["spp"], w["depth"], 1000, 0, 1, 0.0), one.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        floor = 1e-3 * float(one.mean().item())
+        rel = (sharded - one).abs() / torch.maximum(one.abs(), torch.tensor(floor, device="cuda"))
+        t4 = {"max_rel_diff_vs_1gpu": float(rel.max().item()), "mean_rel_diff": float(rel.mean().item()),
+              "bound": 1e-5, "ok": bool(rel.max().item() <= 1e-5),
+              "note": "per-pixel |N-GPU - 1-GPU| / max(|1-GPU|, 1e-3 x mean radiance); same paths, float summation order differs"}
+    if dist is not None:
+        dist.barrier()
 
     # end to end through the host-buffer C-ABI call (film copied to pinned host memory every step)
     for _ in range(1):
@@ -407,8 +463,23 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # the dominant kernel timed ALONE: one more step with a single sub-pool, so that no launch of another stream overlaps the
+    # extend launches whose CUDA-event durations are summed (with 2 sub-pools the sums exceed the wall time)
+    alone = None
+    if w["integrator"] in ("pt", "whitted") and world == 1:
+        os.environ["WRT_SUBPOOLS"] = "1"
+        try:
+            render_dev(film); torch.cuda.synchronize()
+            scene.reset_stats(); render_dev(film); torch.cuda.synchronize()
+            sa = scene.stats()
+            alone = {"extend_ms": sa.extend_ms, "extend_rays": float(sa.extend_rays), "launches": int(sa.extend_launches),
+                     "render_ms": sa.last_render_ms}
+        finally:
+            del os.environ["WRT_SUBPOOLS"]
+
     value = rays / ms / 1e3
     total_samples = samples_per_step * args.steps * world
+    unit_name = "iterations" if w["integrator"] == "bdpt" else "spp"
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None,
@@ -416,8 +487,10 @@ def main():
         "config": {"workload": w["desc"], "integrator": w["integrator"], "traversal": "pruned (bit-exact vs exact, tests/test_gpu_traversal.py)",
                    "per_gpu": ("full frame, %d %s per GPU, disjoint RNG streams; films summed by one NCCL reduce" if not strong else
                                "full frame, %d %s in total, dealt round-robin to the GPUs (same grid and seed as 1 GPU); films summed by one NCCL reduce") %
-                              (w.get("spp", w.get("iterations")), "iterations" if w["integrator"] == "bdpt" else "spp"),
-                   "l2": "inputs larger than L2: the path pool (2^24 slots x 176 B in 2 concurrent sub-pools) is rewritten every bounce; the scene is meant to stay L2-resident",
+                              (w.get("spp", w.get("iterations")), unit_name),
+                   "l2": "inputs larger than L2: the path pool (up to 2^26 slots x 176 B in concurrent sub-pools) is rewritten every bounce; the scene is meant to stay L2-resident",
+                   "loop": "device-driven: every iteration reads its queue length from the counter bank its predecessor wrote; the host enqueues iterations "
+                           "back to back and polls one batch late (pt_wavefront.cu)",
                    "prims": int(sc.n_prims), "kd_build_s": round(kd_build_s, 2), "upload_s": round(upload_s, 2)},
         "samples_per_s": total_samples / (ms / 1e3), "rays_per_sample": rays / total_samples,
         "mean_radiance": mean_radiance,
@@ -427,37 +500,62 @@ def main():
                 "h2d_bytes_per_step": int(C_sizeof_inputs(W, w)), "d2h_bytes_per_step": int(npix * 12),
                 "ms_per_step": 1e3 * e2e_s / args.steps},
     }
+    if world > 1:
+        line["reduce_ms"] = reduce_ms / args.steps
+        line["reduce"] = {"ms_per_step": reduce_ms / args.steps, "bytes": int(npix * 12), "what": "torch.distributed.reduce(SUM, fp32 film -> rank 0) over NCCL, "
+                          "CUDA events around the collective, max over ranks (includes waiting for the slowest rank)"}
+        line["t4_self_check"] = t4
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    if b_ray is not None and ext_ms > 0:
-        # dominant kernel = closest-hit traversal (k_pt_extend): algorithmic bytes of the reference-semantics
-        # traversal of the rays it traced / its own CUDA-event time
-        achieved = (ext_rays * b_ray) / (ext_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "k_pt_extend<pruned>", "achieved": achieved, "peak": peak,
-                            "note": "launch durations are CUDA-event times of launches that overlap with the other sub-pool's kernels (2 streams), so this is a lower bound of the kernel's stand-alone rate",
-                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                            "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": (NCU_DRAM_BYTES_PER_RAY.get(args.workload) or 0) * ext_rays / max(ext_launches, 1) or None,
-                            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per ray of one ncu --set full capture "
-                                              "(%s) x rays per launch" % NCU_SOURCE.get(args.workload, "none for this workload"),
-                            "frac_note": "frac uses the REFERENCE-semantics bytes SURVEY 8(d) defines (full traversal, no early exit); PRUNED traversal "
-                                         "skips most of that work, so frac > 1 is possible and says how much of the reference's traffic is avoided, not a "
-                                         "bandwidth; frac_own_work = the kernels' own algorithmic bytes / peak.  The scene is L2-resident and the "
-                                         "kernel is bound by issue slots and L2 latency (profiles/): DRAM traffic per launch is in `traffic`",
-                            "frac_own_work": (ext_rays * b_ray_k) / (ext_ms * 1e-3) / 1e9 / peak,
-                            "bytes_per_ray": b_ray, "visits_per_ray_reference_semantics": visits,
-                            "kernel_own_work": {"visits_per_ray": visits_k, "bytes_per_ray": b_ray_k,
-                                                "achieved_GBps": (ext_rays * b_ray_k) / (ext_ms * 1e-3) / 1e9,
-                                                "note": "what the PRUNED kernels actually fetch (not counting skipped nodes): "
-                                                        "pruning removes most of the reference-semantics bytes, which is why frac can exceed 1"},
-                            "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
-                            "rays_per_launch": ext_rays / max(ext_launches, 1),
-                            "kernel_share_of_step": ext_ms / ms,
-                            "extend_mrays_per_s": ext_rays / ext_ms / 1e3}
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    nm = ncu_metrics(args.workload) or {}
+    if b_ray is not None and ext_ms > 0 and not sc_small_tree(scene, w):
+        # dominant kernel = closest-hit traversal (k_pt_extend).  It is bound by ISSUE SLOTS and by the latency of dependent L1/L2
+        # fetches, not by DRAM (the committed ncu capture: DRAM a few % of peak), so `bound` says so.  `achieved` / `frac` are the
+        # kernel's OWN algorithmic bytes (what the PRUNED traversal fetches: 32 B per node visit, 48 B per leaf record, 40 B per ray)
+        # over its launch durations, timed ALONE where possible; the reference-semantics figure SURVEY 8(d) defines is kept beside it.
+        t_ms, t_rays, t_launch = (alone["extend_ms"], alone["extend_rays"], alone["launches"]) if alone else (ext_ms, ext_rays, ext_launches)
+        own = (t_rays * b_ray_k) / (t_ms * 1e-3) / 1e9
+        line["roofline"] = {
+            "bound": "issue", "kernel": "k_pt_extend<pruned>",
+            "achieved": own, "peak": peak, "unit": "GB/s", "frac": own / peak, "peak_source": peak_src,
+            "what": "own-work algorithmic bytes (bytes_per_ray x rays) / summed CUDA-event durations of the extend launches of one step run with a "
+                    "single sub-pool (no overlapping stream); against the measured HBM copy peak as the common yardstick — the binding limit is the "
+                    "issue rate: see `issue`",
+            "bytes_per_ray": b_ray_k, "visits_per_ray": visits_k,
+            "avg_launch_ms": t_ms / max(t_launch, 1), "launches": int(t_launch), "rays_per_launch": t_rays / max(t_launch, 1),
+            "extend_mrays_per_s": t_rays / t_ms / 1e3,
+            "traffic": (nm.get("dram_bytes_per_ray") or 0) * t_rays / max(t_launch, 1) or None,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per ray of the committed ncu --set full capture (%s) x rays per launch" % nm.get("source", "none for this workload"),
+            "issue": {"issue_active_pct": nm.get("issue_active_pct"), "threads_per_inst": nm.get("threads_per_inst"),
+                      "useful_issue_frac": (nm["issue_active_pct"] / 100.0 * nm["threads_per_inst"] / 32.0) if nm.get("issue_active_pct") and nm.get("threads_per_inst") else None,
+                      "warp_inst_per_ray": nm.get("warp_inst_per_ray"), "source": nm.get("source"),
+                      "note": "issue slots in use x lanes doing useful work: the fraction of the SM's instruction throughput that advances rays"},
+            "in_step": {"extend_ms_summed": ext_ms / args.steps, "kernel_share_of_step": ext_ms / ms,
+                        "note": "summed launch durations inside the timed step; sub-pool streams overlap, so the share can exceed 1"},
+            "reference_semantics": {"bytes_per_ray": b_ray, "visits_per_ray": visits, "achieved_GBps": (t_rays * b_ray) / (t_ms * 1e-3) / 1e9,
+                                    "ratio_to_peak": (t_rays * b_ray) / (t_ms * 1e-3) / 1e9 / peak,
+                                    "note": "SURVEY 8(d): bytes of the reference's FULL traversal (no early exit) of the same rays / this kernel's time; "
+                                            "a ratio above 1 is work avoided by the bit-exact pruning, not bandwidth"}}
+    elif w["integrator"] == "bdpt" and shade_ms > 0:
+        # C4: 38 primitives — traversal is a handful of steps; the dominant kernels are the shade kernels (camera vertices connect to
+        # every stored light vertex), which stream path state and light vertices from HBM: a memory roofline.
+        per_step_closest, per_step_shadow = closest_rays / args.steps, shadow_rays / args.steps
+        bytes_step = per_step_closest * (32 + 16 + 16 + 4 + 8 + 72) + per_step_shadow * (64 + 52 + 52)
+        ach = bytes_step * args.steps / (shade_ms * 1e-3) / 1e9
+        line["roofline"] = {
+            "bound": "hbm", "kernel": "k_bdpt_camera_shade + k_bdpt_light_shade", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "peak_source": peak_src,
+            "what": "algorithmic bytes of the shade kernels: per path vertex 76 B of state read + 72 B written; per connection 64 B light vertex read, "
+                    "52 B queue entry written and 52 B read back by the connection kernel / summed CUDA-event durations of the shade launches",
+            "avg_launch_ms": shade_ms / max(ext_launches, 1), "launches": int(ext_launches),
+            "kernel_share_of_step": shade_ms / ms, "traffic": None,
+            "stage_ms_per_step": {"extend": ext_ms / args.steps, "shade": shade_ms / args.steps, "connect+di": shadow_ms / args.steps},
+            "traversal_own_work": {"visits_per_ray": visits_k, "bytes_per_ray": b_ray_k}}
     else:
         line["roofline"] = None
     if world == 1 and not args.no_cpu_baseline:
@@ -466,6 +564,11 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def sc_small_tree(scene, w):
+    """Trees under 512 nodes (C4's Cornell box) run the plain per-thread traversal; their dominant kernel is the shade kernel."""
+    return w["integrator"] == "bdpt"
 
 
 def C_sizeof_inputs(W, w):
@@ -483,9 +586,10 @@ def cpu_baseline(w, unit):
         rw["row_stride"] *= 2
     res, build_s = run_reference(rw, 1, 0, 1)
     rays, samples, secs = res[0]
+    what = ("1 spp on every %d-th row of the %dx%d frame" % (rw["row_stride"], rw["width"], rw["height"])) if rw["integrator"] == "pt" else \
+           ("1 %s of the whole %dx%d frame" % ("iteration" if rw["integrator"] == "bdpt" else "spp", rw["width"], rw["height"]))
     return {"value": rays / secs / 1e6, "unit": unit, "cores": 1, "kind": "reference",
-            "sample": "1 spp on every %d-th row of the %dx%d frame (%d rays, %.1f s); reference KD build %.1f s not timed"
-                      % (rw["row_stride"], rw["width"], rw["height"], rays, secs, build_s),
+            "sample": "%s (%d rays, %.1f s); reference KD build %.1f s not timed" % (what, rays, secs, build_s),
             "samples_per_s": samples / secs, "rays_per_sample": rays / max(samples, 1)}
 
 

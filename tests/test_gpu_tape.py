@@ -77,9 +77,15 @@ def test_pt_follows_the_reference_path_for_path_on_the_device(wrt, have_ref, nam
     film, tape, rgb, draws = ref.render_pt_tape(spp, depth, seed=5489 + spp, stride=96)
     scene.set_rng_tape(tape, 96)
     mine = scene.render_pt(hs.camera(), wrt.PtParams(res, res, spp, depth, 1, 0, 1, 0.0))
-    # torus.scene: single-sample radiances span 0 .. 1e3 (paths through glass that find the emitter), so ONE path that
-    # branches differently can move the rRMSE of a 1-spp film; the pixel fraction is the robust figure there
-    check("PT %s %d spp" % (name, spp), mine, film, rrmse=0.01 if name != "torus" else 0.05)
+    # torus.scene: coordinates in the thousands (float spacing 1e-4), refraction chains through the glass cube and
+    # single-sample radiances from 0 to 1e3 x the mean (paths that find the far-away emitter): an ulp of difference in
+    # sinf / cosf moves a hit point by 1e-4 and is amplified along the chain, so about 1 SAMPLE in 1000 ends somewhere else
+    # (measured: 0.10 % of the pixels at 1 spp, 1.55 % at 16 spp = 1 - (1 - 0.001)^16), and one such path can move the rRMSE
+    # of the whole film.  Bar for this scene: at most 0.3 % of the samples (=> pixels: 1 - (1 - 0.003)^spp), rRMSE <= 5 %.
+    if name == "torus":
+        check("PT %s %d spp" % (name, spp), mine, film, frac=1.0 - (1.0 - 0.003) ** spp, rrmse=0.05)
+    else:
+        check("PT %s %d spp" % (name, spp), mine, film, rrmse=0.01)
     # sharded over 2 "GPUs": same tape, same film (T4 with deterministic numbers)
     parts = sum(scene.render_pt(hs.camera(), wrt.shard_pt(wrt.PtParams(res, res, spp, depth, 1, 0, 1, 0.0), g, 2)) for g in range(2)) if spp >= 2 else mine
     assert np.allclose(parts, mine, rtol=1e-4, atol=1e-6)

@@ -55,8 +55,10 @@ __device__ __forceinline__ void conn_store(const ShadowQueue& q, size_t pos, con
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_bdpt_light_init(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B, uint32_t* queue)
+k_bdpt_light_init(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B, uint32_t* queue, unsigned long long* ctr, int first_parity)
 {
+    // the bank the phase's first iteration reads (device-driven loop, wavefront.h)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr[(first_parity ^ 1) * WF_BANK + WF_NEXT_COUNT] = P.n_paths; ctr[(first_parity ^ 1) * WF_BANK + WF_GEN_COUNT] = 0; }
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_paths; i += gridDim.x * blockDim.x) {
         RayIn r; BdptPath st;
         bdpt_light_generate(sc, P, i, r, st);
@@ -67,8 +69,9 @@ k_bdpt_light_init(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B, u
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_bdpt_camera_init(BdptParams P, DevCamera cam, PathPool pool, BdptBuffers B, uint32_t* queue)
+k_bdpt_camera_init(BdptParams P, DevCamera cam, PathPool pool, BdptBuffers B, uint32_t* queue, unsigned long long* ctr, int first_parity)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr[(first_parity ^ 1) * WF_BANK + WF_NEXT_COUNT] = P.n_paths; ctr[(first_parity ^ 1) * WF_BANK + WF_GEN_COUNT] = 0; }
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_paths; i += gridDim.x * blockDim.x) {
         RayIn r; BdptPath st;
         bdpt_camera_generate(P, cam, i, r, st);
@@ -79,9 +82,11 @@ k_bdpt_camera_init(BdptParams P, DevCamera cam, PathPool pool, BdptBuffers B, ui
 
 __global__ void __launch_bounds__(kBlock)
 k_bdpt_light_shade(DevSceneView sc, BdptParams P, DevCamera cam, PathPool pool, BdptBuffers B,
-                   const uint32_t* __restrict__ queue_in, size_t n, uint32_t* __restrict__ queue_out,
-                   unsigned long long* counters)
+                   const uint32_t* __restrict__ queue_in, uint32_t* __restrict__ queue_out,
+                   unsigned long long* ctr, int parity)
 {
+    const size_t n = wf_queue_n(wf_prev(ctr, parity));
+    unsigned long long* counters = wf_cur(ctr, parity);
     size_t base;
     while (next_chunk(&counters[WF_WORK2], n, base)) {
         const size_t e = base + (threadIdx.x & 31);
@@ -116,8 +121,10 @@ k_bdpt_light_shade(DevSceneView sc, BdptParams P, DevCamera cam, PathPool pool, 
 
 __global__ void __launch_bounds__(kBlock)
 k_bdpt_camera_shade(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B, const uint32_t* __restrict__ queue_in,
-                    size_t n, uint32_t* __restrict__ queue_out, float* __restrict__ film, unsigned long long* counters)
+                    uint32_t* __restrict__ queue_out, float* __restrict__ film, unsigned long long* ctr, int parity)
 {
+    const size_t n = wf_queue_n(wf_prev(ctr, parity));
+    unsigned long long* counters = wf_cur(ctr, parity);
     size_t base;
     while (next_chunk(&counters[WF_WORK2], n, base)) {
         const size_t e = base + (threadIdx.x & 31);
@@ -177,9 +184,12 @@ k_bdpt_camera_shade(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B,
 // is visible, otherwise the outer weight is 0) the BSDF-sampled closest-hit ray.
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock)
-k_bdpt_di(DevSceneView sc, const float4* __restrict__ di, float* __restrict__ film, float scale, unsigned long long* counters)
+k_bdpt_di(DevSceneView sc, const float4* __restrict__ di, float* __restrict__ film, float scale, unsigned long long* ctr, int parity)
 {
+    unsigned long long* counters = wf_cur(ctr, parity);
     const size_t n = (size_t)counters[WF_AUX_COUNT];
+    if (n == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr[WF_TOTAL_SHADOW], (unsigned long long)n);
     size_t base;
     unsigned long long extra = 0;
     while (next_chunk(&counters[WF_WORK4], n, base)) {
@@ -205,7 +215,7 @@ k_bdpt_di(DevSceneView sc, const float4* __restrict__ di, float* __restrict__ fi
             }
         }
     }
-    if (extra) atomicAdd(&counters[WF_AUX2_COUNT], extra);
+    if (extra) atomicAdd(&ctr[WF_TOTAL_CLOSEST], extra);     // the BSDF-sampled closest-hit rays of getDirectIllumination
 }
 
 __global__ void k_transpose_film(const float* __restrict__ in, float* __restrict__ out, int n)
@@ -351,55 +361,66 @@ static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bd
     int timed = 0;
     sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
     WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
+    // A sub-path has at most max_len vertices, so a phase is at most max_len + 1 iterations: the loop is enqueued whole,
+    // every kernel reads its queue length from the bank its predecessor wrote, and nothing is read back until the end
+    // (r1 synchronised and copied counters after each of ~2 x 11 iterations per batch).
+    const int phase_iters = P.max_len + 1;
+    int iter = 0;                                             // global iteration index: parity selects the counter bank
 
     for (int done_iters = 0; done_iters < my_iters; done_iters += batch) {
         const int nb = std::min(batch, my_iters - done_iters);
         P.iteration = p->iter_first + done_iters * stride;
         P.n_paths = P.n_pixels * (unsigned)nb;
         for (int phase = 0; phase < 2; phase++) {
-            if (phase == 0) k_bdpt_light_init<<<g_li, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[0]);
-            else k_bdpt_camera_init<<<g_ci, kBlock, 0, st>>>(P, dc, wf->pool, Bv, wf->queue[0]);
+            int cur = 0;
+            if (phase == 0) k_bdpt_light_init<<<g_li, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[0], wf->counters, iter & 1);
+            else k_bdpt_camera_init<<<g_ci, kBlock, 0, st>>>(P, dc, wf->pool, Bv, wf->queue[0], wf->counters, iter & 1);
             WRT_CUDA(cudaGetLastError());
             sc->stats.kernel_launches += 1;
-            size_t n = P.n_paths;
-            int cur = 0;
-            while (n > 0) {
+            for (int it = 0; it < phase_iters; it++, iter++) {
+                const int par = iter & 1;
                 const bool time_it = timed < kMaxTimed;
                 if (time_it && 4 * (timed + 1) > wf->n_ev) { rc = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (rc) return rc; }
                 cudaEvent_t* ev = time_it ? &wf->ev[4 * timed] : nullptr;
-                WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), st));
+                WRT_CUDA(cudaMemsetAsync(wf->counters + par * WF_BANK, 0, WF_BANK * sizeof(unsigned long long), st));
                 if (ev) cudaEventRecord(ev[0], st);
-                if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-        else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters);
-                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
-                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch);
+                if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, 0);
+                else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, 0);
+                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0);
+                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0);
                 if (ev) cudaEventRecord(ev[1], st);
                 if (phase == 0)
-                    k_bdpt_light_shade<<<g_ls, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, Bv, wf->queue[cur], n, wf->queue[cur ^ 1], wf->counters);
+                    k_bdpt_light_shade<<<g_ls, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, Bv, wf->queue[cur], wf->queue[cur ^ 1], wf->counters, par);
                 else
-                    k_bdpt_camera_shade<<<g_cs, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[cur], n, wf->queue[cur ^ 1], d_film, wf->counters);
+                    k_bdpt_camera_shade<<<g_cs, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[cur], wf->queue[cur ^ 1], d_film, wf->counters, par);
                 if (ev) cudaEventRecord(ev[2], st);
-                if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
-        else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters);
-                else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
-                else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
+                if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par);
+                else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par);
+                else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch);
+                else k_pt_shadow<false><<<g_sh_e, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch);
                 if (phase == 1) {
-                    if (pruned) k_bdpt_di<true><<<g_di_p, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters);
-                    else k_bdpt_di<false><<<g_di_e, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters);
+                    if (pruned) k_bdpt_di<true><<<g_di_p, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters, par);
+                    else k_bdpt_di<false><<<g_di_e, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters, par);
                 }
                 if (ev) { cudaEventRecord(ev[3], st); timed++; }
                 WRT_CUDA(cudaGetLastError());
-                WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters, WF_PER_ITER * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-                WRT_CUDA(cudaStreamSynchronize(st));
-                sc->stats.closest_rays += n + wf->h_counters[WF_AUX2_COUNT];
-                sc->stats.extend_launches += 1; sc->stats.extend_rays += n;
-                sc->stats.shadow_rays += wf->h_counters[WF_SHADOW_COUNT] + wf->h_counters[WF_AUX_COUNT];
                 sc->stats.kernel_launches += 3 + (phase == 1 ? 1 : 0);
-                n = (size_t)wf->h_counters[WF_NEXT_COUNT];
                 cur ^= 1;
+                if ((it & 15) == 15 && it + 1 < phase_iters) {      // very long paths allowed (max_len > 15): look once every 16 iterations
+                    WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters + par * WF_BANK, WF_BANK * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+                    WRT_CUDA(cudaStreamSynchronize(st));
+                    if (wf_queue_n(wf->h_counters) == 0) { iter++; break; }
+                }
             }
         }
         sc->stats.samples += P.n_paths;
+    }
+    {   // ray counts of the render: accumulated on the device, read once
+        unsigned long long h[3];
+        WRT_CUDA(cudaMemcpyAsync(h, &wf->counters[WF_TOTAL_CLOSEST], sizeof h, cudaMemcpyDeviceToHost, st));
+        WRT_CUDA(cudaStreamSynchronize(st));
+        sc->stats.closest_rays += h[0]; sc->stats.shadow_rays += h[1];
+        sc->stats.extend_rays += h[0]; sc->stats.extend_launches += h[2];
     }
     wavefront_sum_stage_times(sc, wf, timed);
     if (counting) {

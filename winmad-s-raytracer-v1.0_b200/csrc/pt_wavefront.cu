@@ -42,8 +42,9 @@ __device__ __forceinline__ void pool_load_data(const PathPool& pool, uint32_t sl
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0, unsigned long long first_sample)
+k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0, unsigned long long first_sample, unsigned long long* ctr)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr[WF_BANK + WF_NEXT_COUNT] = n0; ctr[WF_BANK + WF_GEN_COUNT] = 0; }   // what iteration 0 (bank 0) reads
     for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n0; s += gridDim.x * blockDim.x) {
         RayIn r; PathData pd;
         pt_generate(P, cam, first_sample + s, r, pd);
@@ -53,10 +54,13 @@ k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in, size_t n,
-           uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* counters,
-           unsigned long long* next_sample, size_t n_gen_in, size_t cap)
+k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in,
+           uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* ctr, int parity,
+           unsigned long long* next_sample, size_t cap)
 {
+    const unsigned long long* prev = wf_prev(ctr, parity);
+    unsigned long long* counters = wf_cur(ctr, parity);
+    const size_t n = wf_queue_n(prev), n_gen_in = (size_t)prev[WF_GEN_COUNT];
     size_t base;
     while (next_chunk(&counters[WF_WORK2], n, base)) {
         const size_t e = base + (threadIdx.x & 31);
@@ -86,7 +90,7 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
         const bool regen = dead && snew < P.total_samples;
         if (regen) pt_generate(P, cam, snew, r, pd);
         const unsigned long long qpos = warp_append(&counters[WF_NEXT_COUNT], alive);
-        const unsigned long long gpos = warp_append(&counters[WF_WORK4], regen);
+        const unsigned long long gpos = warp_append(&counters[WF_GEN_COUNT], regen);
         if (alive) { pool_store(pool, slot, r, pd); queue_out[qpos] = slot; }                 // continuing paths: front
         if (regen) { pool_store(pool, slot, r, pd); queue_out[cap - 1 - gpos] = slot; }       // new camera rays: back
     }
@@ -109,8 +113,9 @@ __device__ __forceinline__ void wh_store(const PathPool& pool, uint32_t slot, co
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_wh_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0, unsigned long long first_sample)
+k_wh_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0, unsigned long long first_sample, unsigned long long* ctr)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr[WF_BANK + WF_NEXT_COUNT] = n0; ctr[WF_BANK + WF_GEN_COUNT] = 0; }
     for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n0; s += gridDim.x * blockDim.x) {
         RayIn r; PathData pd;
         pt_generate(P, cam, first_sample + s, r, pd);
@@ -120,10 +125,13 @@ k_wh_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0
 }
 
 __global__ void __launch_bounds__(kBlock)
-k_wh_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in, size_t n,
-           uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* counters,
-           unsigned long long* next_sample, size_t n_gen_in, size_t cap, WhittedPending pend, int levels)
+k_wh_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in,
+           uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* ctr, int parity,
+           unsigned long long* next_sample, size_t cap, WhittedPending pend, int levels)
 {
+    const unsigned long long* prev = wf_prev(ctr, parity);
+    unsigned long long* counters = wf_cur(ctr, parity);
+    const size_t n = wf_queue_n(prev), n_gen_in = (size_t)prev[WF_GEN_COUNT];
     size_t base;
     while (next_chunk(&counters[WF_WORK2], n, base)) {
         const size_t e = base + (threadIdx.x & 31);
@@ -179,7 +187,7 @@ k_wh_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
             w = 1.f; pixel = pd.pixel; rng = pd.rng; dep = 0; pending = 0;
         }
         const unsigned long long qpos = warp_append(&counters[WF_NEXT_COUNT], alive);
-        const unsigned long long gpos = warp_append(&counters[WF_WORK4], regen);
+        const unsigned long long gpos = warp_append(&counters[WF_GEN_COUNT], regen);
         if (alive) { wh_store(pool, slot, r, w, pixel, rng, dep, pending); queue_out[qpos] = slot; }
         if (regen) { wh_store(pool, slot, r, w, pixel, rng, dep, pending); queue_out[cap - 1 - gpos] = slot; }
     }
@@ -220,6 +228,8 @@ static int wavefront_alloc(wrt_wavefront* wf, int capacity)
     WRT_CUDA(cudaStreamCreateWithFlags(&wf->stream, cudaStreamNonBlocking));
     { int rc = ensure_trav_scratch(&wf->trav_scratch, &wf->trav_scratch_bytes); if (rc) return rc; }
     WRT_CUDA(cudaEventCreateWithFlags(&wf->join_ev, cudaEventDisableTiming));
+    WRT_CUDA(cudaEventCreateWithFlags(&wf->poll_ev[0], cudaEventDisableTiming));
+    WRT_CUDA(cudaEventCreateWithFlags(&wf->poll_ev[1], cudaEventDisableTiming));
     return WRT_OK;
 }
 
@@ -297,6 +307,7 @@ static void wavefront_free(wrt_wavefront* wf)
     delete[] wf->ev;
     if (wf->stream) cudaStreamDestroy(wf->stream);
     if (wf->join_ev) cudaEventDestroy(wf->join_ev);
+    for (int i = 0; i < 2; i++) if (wf->poll_ev[i]) cudaEventDestroy(wf->poll_ev[i]);
     delete wf;
 }
 
@@ -365,8 +376,17 @@ static void pt_plan(const PtParams& P, PtPlan& plan, bool whitted = false)
     for (int j = 0; j < k; j++) plan.cap[j] = (int)std::max<unsigned long long>(per, 1024ull);
 }
 
+// Host-side view of one sub-pool's device-driven loop.  Iterations are enqueued in batches; after every batch the bank
+// the last iteration wrote is copied to one of two pinned slots, so the host learns the queue length one batch late
+// and never stalls the stream to find out.
 struct SubState {
-    wrt_wavefront* wf; size_t n; size_t n_gen; int cur; bool in_flight; int timed; int index;
+    wrt_wavefront* wf; int index;
+    int iter;                 // iterations enqueued so far (parity of the next one = iter & 1)
+    int batches;              // batches enqueued so far
+    int polled;               // batches whose result has been read
+    size_t last_n;            // queue length seen by the most recent poll
+    bool done;
+    int timed;
 };
 
 // Per-sub-pool pending lists of the Whitted integrator: (max_depth + 1) levels x capacity x 32 bytes.
@@ -441,12 +461,12 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
         const unsigned long long left = P.total_samples - first;
         const unsigned n0 = (unsigned)std::min<unsigned long long>((unsigned long long)plan.cap[j], left);
         WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_COUNTERS * sizeof(unsigned long long), st));
-        if (n0 && whitted) k_wh_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first);
-        else if (n0) k_pt_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first);
+        if (whitted) k_wh_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first, wf->counters);
+        else k_pt_init<<<g_init, kBlock, 0, st>>>(P, dc, wf->pool, wf->queue[0], n0, first, wf->counters);
         WRT_CUDA(cudaGetLastError());
-        sub[j].n = n0; sub[j].n_gen = 0; sub[j].cur = 0; sub[j].in_flight = false; sub[j].timed = 0; sub[j].index = j;
+        sub[j].index = j; sub[j].iter = 0; sub[j].batches = 0; sub[j].polled = 0; sub[j].last_n = n0; sub[j].done = n0 == 0; sub[j].timed = 0;
         first += n0;
-        sc->stats.kernel_launches += n0 ? 1 : 0;
+        sc->stats.kernel_launches += 1;
     }
     unsigned long long* next_sample = &sub[0].wf->counters[WF_NEXT_SAMPLE];
     WRT_CUDA(cudaMemcpyAsync(next_sample, &first, sizeof first, cudaMemcpyHostToDevice, st));
@@ -455,68 +475,96 @@ static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_p
     for (int j = 0; j < plan.k; j++) WRT_CUDA(cudaStreamWaitEvent(sub[j].wf->stream, sc->ev_fork, 0));
 
     const int kMaxTimed = 2048;
-    sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
-    unsigned long long iters = 0;
+    const bool regenerates = P.total_samples > first;       // some slot will take a second camera sample
+    // Without regeneration a path slot lives for at most max_depth + 1 vertices (+ the emitter hit that ends it): the number
+    // of iterations is known up front and nothing has to be read back at all.
+    const int fixed_iters = regenerates ? 0 : (whitted ? 0 : P.max_depth + 2);
 
-    auto launch = [&](SubState& s) -> int {
+    // one iteration of sub-pool s: extend -> shade -> shadow on the sub-pool's stream, all lengths read on the device
+    auto enqueue_iteration = [&](SubState& s) -> int {
         wrt_wavefront* wf = s.wf;
         cudaStream_t q = wf->stream;
+        const int par = s.iter & 1, cur = s.iter & 1;           // queue[cur] is consumed, queue[cur ^ 1] produced
+        const size_t cap = (size_t)wf->capacity;
         const bool time_it = s.timed < kMaxTimed;
         if (time_it && 4 * (s.timed + 1) > wf->n_ev) { int r = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (r) return r; }
         cudaEvent_t* ev = time_it ? &wf->ev[4 * s.timed] : nullptr;
-        const size_t n = s.n; const int cur = s.cur; const size_t ng = s.n_gen; const size_t cap = (size_t)wf->capacity;
-        WRT_CUDA(cudaMemsetAsync(wf->counters, 0, WF_PER_ITER * sizeof(unsigned long long), q));
+        WRT_CUDA(cudaMemsetAsync(wf->counters + par * WF_BANK, 0, WF_BANK * sizeof(unsigned long long), q));
         if (ev) cudaEventRecord(ev[0], q);
-        if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, ng, cap);
-        else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, ng, cap);
-        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch, ng, cap);
-        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], n, wf->counters, (float4*)wf->trav_scratch, ng, cap);
+        if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, cap);
+        else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, cap);
+        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, cap);
+        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, cap);
         if (ev) cudaEventRecord(ev[1], q);
-        if (whitted) k_wh_shade<<<g_wshade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
-                                                            d_film, wf->counters, next_sample, ng, cap, wh_pend[s.index], wh_levels);
-        else k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], n, wf->queue[cur ^ 1], wf->shadow,
-                                                   d_film, wf->counters, next_sample, ng, cap);
+        if (whitted) k_wh_shade<<<g_wshade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], wf->queue[cur ^ 1], wf->shadow,
+                                                            d_film, wf->counters, par, next_sample, cap, wh_pend[s.index], wh_levels);
+        else k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], wf->queue[cur ^ 1], wf->shadow,
+                                                   d_film, wf->counters, par, next_sample, cap);
         if (ev) cudaEventRecord(ev[2], q);
-        if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
-        else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters);
-        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
-        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, (float4*)wf->trav_scratch);
+        if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, par);
+        else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, par);
+        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch);
+        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch);
         if (ev) { cudaEventRecord(ev[3], q); s.timed++; }
         WRT_CUDA(cudaGetLastError());
-        WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters, WF_PER_ITER * sizeof(unsigned long long), cudaMemcpyDeviceToHost, q));
-        s.in_flight = true;
+        sc->stats.kernel_launches += 3;
+        s.iter++;
         return WRT_OK;
     };
-    auto complete = [&](SubState& s) -> int {
+    // a batch of iterations, then the bank the last one wrote -> pinned slot (batch & 1), marked by an event
+    auto enqueue_batch = [&](SubState& s) -> int {
+        // large queues: one iteration per batch (an iteration takes milliseconds, nothing to gain); small ones: four,
+        // so that short frames (torus.scene as shipped: 512 x 512 x 1 spp) never wait for the host
+        const int n_it = s.last_n > (1u << 20) ? 1 : 4;
+        for (int b = 0; b < n_it; b++) { int r = enqueue_iteration(s); if (r) return r; }
         wrt_wavefront* wf = s.wf;
-        WRT_CUDA(cudaStreamSynchronize(wf->stream));
-        sc->stats.closest_rays += s.n;
-        sc->stats.extend_launches += 1; sc->stats.extend_rays += s.n;
-        sc->stats.shadow_rays += wf->h_counters[WF_SHADOW_COUNT];
-        sc->stats.kernel_launches += 3;
-        s.n_gen = (size_t)wf->h_counters[WF_WORK4];
-        s.n = (size_t)wf->h_counters[WF_NEXT_COUNT] + s.n_gen;
-        s.cur ^= 1;
-        s.in_flight = false;
+        const int slot = s.batches & 1;
+        const int last_par = (s.iter - 1) & 1;
+        WRT_CUDA(cudaMemcpyAsync(wf->h_counters + slot * WF_BANK, wf->counters + last_par * WF_BANK, WF_BANK * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, wf->stream));
+        WRT_CUDA(cudaEventRecord(wf->poll_ev[slot], wf->stream));
+        s.batches++;
         return WRT_OK;
     };
 
-    for (int j = 0; j < plan.k; j++) if (sub[j].n > 0) { rc = launch(sub[j]); if (rc) return rc; }
-    for (;;) {
-        bool any = false;
-        for (int j = 0; j < plan.k; j++) {
-            if (!sub[j].in_flight) continue;
-            any = true;
-            rc = complete(sub[j]); if (rc) return rc;
-            if (sub[j].n > 0) { rc = launch(sub[j]); if (rc) return rc; }
+    if (fixed_iters > 0) {
+        for (int j = 0; j < plan.k; j++)
+            if (!sub[j].done) for (int b = 0; b < fixed_iters; b++) { rc = enqueue_iteration(sub[j]); if (rc) return rc; }
+    } else {
+        // two batches in flight per sub-pool; whenever the older one's result is in, decide whether to enqueue another
+        for (int j = 0; j < plan.k; j++) if (!sub[j].done) { rc = enqueue_batch(sub[j]); if (rc) return rc; }
+        for (int j = 0; j < plan.k; j++) if (!sub[j].done) { rc = enqueue_batch(sub[j]); if (rc) return rc; }
+        unsigned long long guard = 0;
+        for (;;) {
+            bool any = false;
+            for (int j = 0; j < plan.k; j++) {
+                SubState& s = sub[j];
+                if (s.done) continue;
+                any = true;
+                const int slot = s.polled & 1;
+                WRT_CUDA(cudaEventSynchronize(s.wf->poll_ev[slot]));
+                s.last_n = wf_queue_n(s.wf->h_counters + slot * WF_BANK);
+                s.polled++;
+                if (s.last_n == 0) { s.done = true; continue; }      // (the younger batch in flight finds empty queues and returns at once)
+                rc = enqueue_batch(s); if (rc) return rc;
+            }
+            if (!any) break;
+            if (++guard > (1ull << 32)) { set_error("wrt_render_pt: runaway iteration count"); return WRT_ERR_CUDA; }
         }
-        if (!any) break;
-        if (++iters > (1ull << 32)) { set_error("wrt_render_pt: runaway iteration count"); return WRT_ERR_CUDA; }
     }
     // join: the caller's stream continues after every sub-pool stream
     for (int j = 0; j < plan.k; j++) {
         WRT_CUDA(cudaEventRecord(sub[j].wf->join_ev, sub[j].wf->stream));
         WRT_CUDA(cudaStreamWaitEvent(st, sub[j].wf->join_ev, 0));
+    }
+    // ray counts of the render: accumulated on the device, read once
+    sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
+    for (int j = 0; j < plan.k; j++) {
+        unsigned long long h[3];
+        WRT_CUDA(cudaMemcpyAsync(h, &sub[j].wf->counters[WF_TOTAL_CLOSEST], sizeof h, cudaMemcpyDeviceToHost, st));
+        WRT_CUDA(cudaStreamSynchronize(st));
+        sc->stats.closest_rays += h[0]; sc->stats.shadow_rays += h[1];
+        sc->stats.extend_rays += h[0]; sc->stats.extend_launches += h[2];
     }
     // stage times: sum of per-launch CUDA-event durations over all sub-pools (launches of different
     // sub-pools overlap, so the sums can exceed the wall time of the render)

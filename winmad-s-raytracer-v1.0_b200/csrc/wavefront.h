@@ -6,22 +6,34 @@
 
 namespace wrt {
 
-// counter block indices (unsigned long long each)
+// Device counter block (unsigned long long each).  The wavefront loops are DEVICE-DRIVEN: every iteration (extend ->
+// shade -> shadow [-> direct illumination]) reads the length of its input queue from the counter bank the previous
+// iteration wrote, so the host can enqueue iterations back to back without reading anything back.
+// Two banks alternate: iteration i writes bank i & 1 and reads bank (i & 1) ^ 1.
 enum {
+    // ---- per-iteration bank (WF_BANK entries) ----
     WF_WORK = 0,        // dynamic work fetch: extend kernel
     WF_WORK2 = 1,       //                     shade kernel
     WF_WORK3 = 2,       //                     shadow kernel
-    WF_NEXT_COUNT = 3,  // entries appended to the next-bounce queue
+    WF_NEXT_COUNT = 3,  // entries appended to the front of the next-bounce queue (continuing paths)
     WF_SHADOW_COUNT = 4,
     WF_AUX_COUNT = 5,   // BDPT direct-illumination entries
-    WF_WORK4 = 6,      // BDPT DI kernel work fetch; PT: regenerated camera rays appended from the back of the queue
+    WF_GEN_COUNT = 6,   // PT: regenerated camera rays appended from the back of the next-bounce queue (BDPT: stays 0)
     WF_AUX2_COUNT = 7,  // BDPT: BSDF-sampled rays traced by the DI kernel
-    WF_PER_ITER = 8,    // counters [0, WF_PER_ITER) are zeroed before every iteration
-    WF_NEXT_SAMPLE = 8, // next camera sample to hand out (path regeneration)
-    WF_LIGHT_VERTS = 9,
-    WF_VISITS = 10,     // +0 inner, +1 leaf, +2 tri, +3 sphere (counting mode)
-    WF_COUNTERS = 16
+    WF_WORK4 = 8,       // BDPT DI kernel work fetch
+    WF_BANK = 12,
+    // ---- persistent part, after the two banks ----
+    WF_PERSIST = 2 * WF_BANK,
+    WF_NEXT_SAMPLE = WF_PERSIST + 0, // next camera sample to hand out (path regeneration)
+    WF_TOTAL_CLOSEST = WF_PERSIST + 1, // rays traced by the extend kernels since the render started
+    WF_TOTAL_SHADOW = WF_PERSIST + 2,  // queries traced by the shadow / DI kernels
+    WF_TOTAL_ITERS = WF_PERSIST + 3,   // iterations that had work
+    WF_VISITS = WF_PERSIST + 4,     // +0 inner, +1 leaf, +2 tri, +3 sphere (counting mode)
+    WF_COUNTERS = WF_PERSIST + 8
 };
+
+// Length of the queue an iteration consumes: continuing paths (front of the queue) + regenerated camera rays (back).
+__host__ __device__ inline size_t wf_queue_n(const unsigned long long* prev) { return (size_t)(prev[WF_NEXT_COUNT] + prev[WF_GEN_COUNT]); }
 
 struct PathPool {            // SoA over `capacity` slots
     wrt_ray* ray;            // 32 B, float4-aligned
@@ -56,6 +68,7 @@ struct wrt_wavefront {
     void* trav_scratch; size_t trav_scratch_bytes;   // pooled scheduler's traversal stacks for this sub-pool's launches
     cudaStream_t stream;                // this sub-pool's own stream (PT runs sub-pools concurrently)
     cudaEvent_t join_ev;
+    cudaEvent_t poll_ev[2];             // device-driven loops: marks the arrival of a batch's counter bank in h_counters
 };
 
 namespace wrt {

@@ -51,24 +51,37 @@ struct ExtendSrc {
     }
 };
 
+// Device-driven iteration (wavefront.h): `ctr` is the counter block, `parity` selects the bank this iteration writes;
+// the queue length comes from the bank the previous iteration wrote.
+__device__ __forceinline__ unsigned long long* wf_cur(unsigned long long* ctr, int parity) { return ctr + parity * WF_BANK; }
+__device__ __forceinline__ const unsigned long long* wf_prev(const unsigned long long* ctr, int parity) { return ctr + (parity ^ 1) * WF_BANK; }
+
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock, WRT_MIN_BLOCKS)
-k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters,
-            float4* scratch, size_t n_gen = 0, size_t cap = 0)
+k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, unsigned long long* ctr, int parity,
+            float4* scratch, size_t cap)
 {
+    const unsigned long long* prev = wf_prev(ctr, parity);
+    const size_t n = wf_queue_n(prev), n_gen = (size_t)prev[WF_GEN_COUNT];
+    if (n == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr[WF_TOTAL_CLOSEST], (unsigned long long)n); atomicAdd(&ctr[WF_TOTAL_ITERS], 1ull); }
     ExtendSrc src = { pool, queue, n_gen, cap };
-    trace_rays<PRUNED>(sc, src, &counters[WF_WORK], n, scratch);
+    trace_rays<PRUNED>(sc, src, &wf_cur(ctr, parity)[WF_WORK], n, scratch);
 }
 
 // Counting-mode variants: EXACT traversal with the reference-semantics visit counters.
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock)
-k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, size_t n, unsigned long long* counters,
-                  size_t n_gen = 0, size_t cap = 0)
+k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, unsigned long long* ctr, int parity, size_t cap)
 {
+    const unsigned long long* prev = wf_prev(ctr, parity);
+    const size_t n = wf_queue_n(prev), n_gen = (size_t)prev[WF_GEN_COUNT];
+    if (n == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr[WF_TOTAL_CLOSEST], (unsigned long long)n); atomicAdd(&ctr[WF_TOTAL_ITERS], 1ull); }
+    unsigned long long* cur = wf_cur(ctr, parity);
     size_t base;
     unsigned long long a = 0, b = 0, c = 0, d = 0;
-    while (next_chunk(&counters[WF_WORK], n, base)) {
+    while (next_chunk(&cur[WF_WORK], n, base)) {
         const size_t e = base + (threadIdx.x & 31);
         if (e >= n) continue;
         const uint32_t slot = queue_slot(queue, e, n_gen, cap);
@@ -80,18 +93,21 @@ k_pt_extend_count(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ q
         pool.hit_t[slot] = t;
         a += vc.inner; b += vc.leaf; c += vc.tri; d += vc.sph;
     }
-    atomicAdd(&counters[WF_VISITS + 0], a); atomicAdd(&counters[WF_VISITS + 1], b);
-    atomicAdd(&counters[WF_VISITS + 2], c); atomicAdd(&counters[WF_VISITS + 3], d);
+    atomicAdd(&ctr[WF_VISITS + 0], a); atomicAdd(&ctr[WF_VISITS + 1], b);
+    atomicAdd(&ctr[WF_VISITS + 2], c); atomicAdd(&ctr[WF_VISITS + 3], d);
 }
 
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock)
-k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters)
+k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* ctr, int parity)
 {
-    const size_t n = (size_t)counters[WF_SHADOW_COUNT];
+    unsigned long long* cur = wf_cur(ctr, parity);
+    const size_t n = (size_t)cur[WF_SHADOW_COUNT];
+    if (n == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr[WF_TOTAL_SHADOW], (unsigned long long)n);
     size_t base;
     unsigned long long a = 0, b = 0, c = 0, d = 0;
-    while (next_chunk(&counters[WF_WORK3], n, base)) {
+    while (next_chunk(&cur[WF_WORK3], n, base)) {
         const size_t e = base + (threadIdx.x & 31);
         if (e >= n) continue;
         const float4 qa = sq.a[e], qb = sq.b[e], qc = sq.c[e];
@@ -108,8 +124,8 @@ k_pt_shadow_count(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, flo
         }
         if (vis) film_add(film, sq.pixel[e], v3(qa.w, qb.w, qc.w), scale);
     }
-    atomicAdd(&counters[WF_VISITS + 0], a); atomicAdd(&counters[WF_VISITS + 1], b);
-    atomicAdd(&counters[WF_VISITS + 2], c); atomicAdd(&counters[WF_VISITS + 3], d);
+    atomicAdd(&ctr[WF_VISITS + 0], a); atomicAdd(&ctr[WF_VISITS + 1], b);
+    atomicAdd(&ctr[WF_VISITS + 2], c); atomicAdd(&ctr[WF_VISITS + 3], d);
 }
 
 struct ShadowSrc {
@@ -150,12 +166,15 @@ struct ShadowSrc {
 
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock, WRT_MIN_BLOCKS)
-k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* counters,
+k_pt_shadow(DevSceneView sc, ShadowQueue sq, float* __restrict__ film, float scale, unsigned long long* ctr, int parity,
             float4* scratch)
 {
-    const size_t n = (size_t)counters[WF_SHADOW_COUNT];
+    unsigned long long* cur = wf_cur(ctr, parity);
+    const size_t n = (size_t)cur[WF_SHADOW_COUNT];
+    if (n == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctr[WF_TOTAL_SHADOW], (unsigned long long)n);
     ShadowSrc src = { sq, film, scale, 0.f, 0.f, 0.f };
-    trace_rays<PRUNED>(sc, src, &counters[WF_WORK3], n, scratch);
+    trace_rays<PRUNED>(sc, src, &cur[WF_WORK3], n, scratch);
 }
 
 }  // namespace wrt
