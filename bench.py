@@ -467,6 +467,7 @@ def main():
     # extend launches whose CUDA-event durations are summed (with 2 sub-pools the sums exceed the wall time)
     alone = None
     if w["integrator"] in ("pt", "whitted") and world == 1:
+        prev_sub = os.environ.get("WRT_SUBPOOLS")
         os.environ["WRT_SUBPOOLS"] = "1"
         try:
             render_dev(film); torch.cuda.synchronize()
@@ -475,7 +476,10 @@ def main():
             alone = {"extend_ms": sa.extend_ms, "extend_rays": float(sa.extend_rays), "launches": int(sa.extend_launches),
                      "render_ms": sa.last_render_ms}
         finally:
-            del os.environ["WRT_SUBPOOLS"]
+            if prev_sub is None:
+                del os.environ["WRT_SUBPOOLS"]
+            else:
+                os.environ["WRT_SUBPOOLS"] = prev_sub
 
     value = rays / ms / 1e3
     total_samples = samples_per_step * args.steps * world

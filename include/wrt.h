@@ -114,6 +114,9 @@ typedef struct {
     double extend_ms, shade_ms, shadow_ms;
     uint64_t extend_launches;  /* closest-hit (extend) kernel launches in the last render */
     uint64_t extend_rays;      /* rays those launches traced */
+    /* multi-GPU renders (wrt_init with more than one device): */
+    double reduce_ms;          /* device time of the film exchange (peer films summed onto device 0) of the last render */
+    uint64_t devices_used;     /* devices the last render ran on */
 } wrt_stats;
 
 typedef struct wrt_scene wrt_scene;           /* device-resident scene */
@@ -124,6 +127,16 @@ const char* wrt_version(void);
 const char* wrt_last_error(void);
 int wrt_device_count(int* count);
 int wrt_set_device(int ordinal);               /* one process per GPU: call once with LOCAL_RANK */
+/* Multi-GPU INSIDE one process (the reference is one process: `ToT <scene> <image> -p`, R/src/main.cpp:29-97).
+ * wrt_init names the devices (device_ids == NULL: 0 .. n_gpus-1; n_gpus <= 0: every visible device) and enables peer access
+ * between them.  Every wrt_scene created afterwards is replicated on all of them, and ONE wrt_render_pt / wrt_render_whitted /
+ * wrt_render_bdpt call (host-film variants) drives them all: samples (iterations) are dealt round-robin to the devices with
+ * the 1-device RNG keys, every device runs its wavefront on its own host thread, and the films — pre-scaled by 1/spp as
+ * SurfaceIntegrator::render's film->scale (surfaceIntegrator.cpp:45) — are summed onto the first device by one kernel that
+ * reads the peers over NVLink.  The image equals the 1-device image up to float summation order.  Level-1 queries run on
+ * the first device.  Without wrt_init the library uses the current device only. */
+int wrt_init(int n_gpus, const int* device_ids);
+int wrt_shutdown(void);                        /* forget the device set (scenes are destroyed by their owners) */
 
 /* ---- host side: the product's own restatement of Scene::init -------------------------------------
  * (not needed by a reference-side shim, which already has Scene, Camera and KDtreeAccel objects) */

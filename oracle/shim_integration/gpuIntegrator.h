@@ -74,6 +74,9 @@ struct GpuSceneBridge {                    // flattens Scene -> wrt_scene_desc, 
         cam.image_plane_dist = c.imagePlaneDist; cam.x_res = c.xResolution; cam.y_res = c.yResolution;
         memcpy(cam.raster_to_world, c.rasterToWorld.m.m, 16 * sizeof(float));   // Camera::setup already ran on the host
         memcpy(cam.world_to_raster, c.worldToRaster.m.m, 16 * sizeof(float));
+        // all GPUs of the box behind the one render() call: WRT_GPUS=8 ./ToT scene out -gp  (scene replicated, samples sharded,
+        // films summed on device 0 over NVLink inside wrt_render_*; without it the library uses the current device)
+        if (const char* g = getenv("WRT_GPUS")) if (wrt_init(atoi(g), nullptr) != WRT_OK) { fprintf(stderr, "wrt: %s\n", wrt_last_error()); return false; }
         if (wrt_scene_create(&d, &dev) != WRT_OK) { fprintf(stderr, "wrt: %s\n", wrt_last_error()); return false; }
         return true;
     }

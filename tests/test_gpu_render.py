@@ -315,3 +315,70 @@ def test_reference_level1_queries_through_the_shim(wrt, tmp_path, which):
     print(r.stdout.strip())
     assert r.returncode == 0, r.stdout + r.stderr
     assert " 0 mismatches" in r.stdout and "level-1 check: %d closest" % 0 not in r.stdout
+
+
+# ---- multi-GPU inside the library (wrt_init): needs >= 2 visible devices (gpurun --gpus 2) -------------------------------
+def _needs_two_gpus(wrt):
+    if wrt.device_count() < 2:
+        pytest.skip("needs at least 2 visible GPUs (gpurun --gpus 2)")
+
+
+@pytest.mark.parametrize("integrator", ["pt", "whitted", "bdpt"])
+def test_multi_gpu_inside_the_library_equals_one_gpu(wrt, integrator):
+    """SURVEY 8(b)/(e), T4 on hardware: wrt_init(n, ids) + ONE wrt_render_* call on n devices (scene replicated by the library,
+    samples / iterations dealt round-robin, films summed on device 0 by the peer-read kernel) against the same call on one
+    device: same RNG keys => same paths; the films differ by float summation order only (<= 1e-5 relative per pixel above a
+    floor of 1e-3 x mean radiance)."""
+    _needs_two_gpus(wrt)
+    n = min(wrt.device_count(), 8)
+    sc = scenes.small_mixed_scene(96, 96)
+    def render():
+        hs = util.host_scene(wrt, sc); scene = wrt.Scene(hs); cam = hs.camera()
+        if integrator == "pt":
+            f = scene.render_pt(cam, wrt.PtParams(96, 96, 16, 5, 7, 0, 1, 0.0))
+        elif integrator == "whitted":
+            f = scene.render_whitted(cam, wrt.PtParams(96, 96, 16, 5, 7, 0, 1, 0.0))
+        else:
+            f = scene.render_bdpt(cam, wrt.BdptParams(96, 96, 8, 0, 10, 3, 7, 0, 1, 0.0, 0))
+        s = scene.stats()
+        scene.close()
+        return f, s
+    one, s1 = render()
+    wrt.init(n)
+    try:
+        many, sn = render()
+    finally:
+        wrt.shutdown(); wrt.set_device(0)
+    assert sn.devices_used == n and sn.samples == s1.samples
+    assert sn.closest_rays == s1.closest_rays and sn.shadow_rays == s1.shadow_rays          # the same paths were traced
+    ok = ~(np.isnan(one) | np.isnan(many))
+    assert np.array_equal(np.isnan(one), np.isnan(many))
+    floor = 1e-3 * float(one[ok].mean())
+    rel = np.abs(many[ok] - one[ok]) / np.maximum(np.abs(one[ok]), floor)
+    print("%s on %d GPUs: max rel diff vs 1 GPU %.2e, film exchange %.3f ms" % (integrator, n, rel.max(), sn.reduce_ms))
+    assert rel.max() <= 1e-5
+
+
+def test_reference_shim_on_all_gpus(wrt, tmp_path):
+    """`WRT_GPUS=n ToT_gpu <scene> <image> -gp`: the UNMODIFIED reference + the INTEGRATION.md shim driving every GPU of the box
+    through one wrt_render_pt call == the same command on one GPU (8-bit images, float summation order may flip a level)."""
+    _needs_two_gpus(wrt)
+    import subprocess, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "ToT_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ToT_gpu not built")
+    res = 64
+    sc = scenes.cornell_box_scene(res, res)
+    scene_file = scenes.write_scene_files(sc, str(tmp_path))
+    para = tmp_path / "parameters.para"
+    para.write_text("#MAX_TRACING_DEPTH\n5\n#SAMPLES_PER_PIXEL\n64\n#l\n8\n#h\n4\n#WIDTH\n%d\n#HEIGHT\n%d\n#x\n5\n#y\n400\n" % (res, res))
+    imgs = []
+    for gpus in (None, str(min(wrt.device_count(), 8))):
+        env = dict(os.environ)
+        if gpus: env["WRT_GPUS"] = gpus
+        out = "o_%s.ppm" % (gpus or "1")
+        r = subprocess.run([exe, scene_file, str(tmp_path / out), "-gp", str(para)], cwd=str(tmp_path), capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0 and "wrt:" not in r.stderr, r.stderr
+        imgs.append(_read_ppm(str(tmp_path / out)).astype(np.int32))
+    assert imgs[0].mean() > 5 and (np.abs(imgs[0] - imgs[1]) > 1).mean() < 0.002

@@ -6,7 +6,7 @@ cd "$(dirname "$0")/../winmad-s-raytracer-v1.0_b200"
 out=libwrt_b200.so
 if [ "$1" = "-o" ]; then out=$2; shift 2; fi
 od=build/variant_$$; mkdir -p $od
-for f in scene_upload trace_kernels pt_wavefront bdpt_wavefront debug_kernels; do
+for f in scene_upload trace_kernels pt_wavefront bdpt_wavefront debug_kernels multi_gpu; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 -Xcompiler -fPIC,-ffp-contract=off -diag-suppress 177 "$@" -c csrc/$f.cu -o $od/$f.cu.o &
 done
 wait

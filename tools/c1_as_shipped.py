@@ -16,6 +16,9 @@ ms = []
 for _ in range(10):
     t0 = time.perf_counter(); film = scene.render_pt(cam, p); wall = (time.perf_counter() - t0) * 1e3
     ms.append((scene.stats().last_render_ms, wall))
+st = scene.stats()
+print("stages of the last frame (summed CUDA-event durations): extend %.3f ms, shade %.3f ms, shadow %.3f ms over %d iterations with work; %d closest + %d shadow rays"
+      % (st.extend_ms, st.shade_ms, st.shadow_ms, st.extend_launches, st.extend_rays, 0))
 print("GPU: device %.3f ms, host wall incl. film copy %.3f ms (median of 10), mean radiance %.5f" % (np.median([m[0] for m in ms]), np.median([m[1] for m in ms]), film.mean()))
 from oracle import refpy
 if refpy.available():

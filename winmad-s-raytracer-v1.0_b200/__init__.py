@@ -82,11 +82,12 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("inner_visits", C.c_uint64), ("leaf_visits", C.c_uint64),
                 ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64), ("last_render_ms", C.c_double),
                 ("last_trace_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
-                ("shadow_ms", C.c_double), ("extend_launches", C.c_uint64), ("extend_rays", C.c_uint64)]
+                ("shadow_ms", C.c_double), ("extend_launches", C.c_uint64), ("extend_rays", C.c_uint64),
+                ("reduce_ms", C.c_double), ("devices_used", C.c_uint64)]
 
 
 EXPORTS = [
-    "wrt_version", "wrt_last_error", "wrt_device_count", "wrt_set_device",
+    "wrt_version", "wrt_last_error", "wrt_device_count", "wrt_set_device", "wrt_init", "wrt_shutdown",
     "wrt_host_scene_load", "wrt_host_scene_from_arrays", "wrt_host_scene_build_kdtree", "wrt_host_scene_desc",
     "wrt_host_scene_camera", "wrt_host_scene_sphere", "wrt_host_scene_free", "wrt_host_scene_save",
     "wrt_host_scene_load_cache", "wrt_camera_setup", "wrt_camera_generate_rays", "wrt_make_rays",
@@ -139,6 +140,19 @@ def device_count():
 
 def set_device(ordinal):
     _check(lib().wrt_set_device(int(ordinal)), "wrt_set_device")
+
+
+def init(n_gpus=0, device_ids=None):
+    """wrt_init: scenes created afterwards are replicated on these devices; one render call drives them all."""
+    ids = None
+    if device_ids is not None:
+        arr = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+        ids, n_gpus = arr, len(device_ids)
+    _check(lib().wrt_init(int(n_gpus), ids), "wrt_init")
+
+
+def shutdown():
+    _check(lib().wrt_shutdown(), "wrt_shutdown")
 
 
 def make_rays(origin_dir6):

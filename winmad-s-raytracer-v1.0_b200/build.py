@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libwrt_b200.so")
 
 CU_SOURCES = ["csrc/scene_upload.cu", "csrc/trace_kernels.cu", "csrc/pt_wavefront.cu",
-              "csrc/bdpt_wavefront.cu", "csrc/debug_kernels.cu"]
+              "csrc/bdpt_wavefront.cu", "csrc/debug_kernels.cu", "csrc/multi_gpu.cu"]
 CPP_SOURCES = ["csrc/scene_layout.cpp", "host/kd_build.cpp", "host/scene_io.cpp", "host/host_api.cpp"]
 HEADERS = ["csrc/dev_scene.h", "csrc/hd_compat.h", "csrc/traverse.cuh", "csrc/scene_layout.h", "csrc/pt_logic.cuh", "csrc/whitted_logic.cuh",
            "csrc/bdpt_logic.cuh", "csrc/warp_utils.cuh", "csrc/wavefront_kernels.cuh", "csrc/trace_persistent.cuh", "csrc/trace_pooled.cuh",

@@ -288,7 +288,7 @@ static int bdpt_batch(const wrt_bdpt_params* p)
     return std::min(batch, my_iters);
 }
 
-static int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* d_film, cudaStream_t st)
+int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* d_film, cudaStream_t st)
 {
     if (!cam || !p || p->width <= 0 || p->height <= 0 || p->iterations <= 0 || p->max_path_length < 1) {
         set_error("wrt_render_bdpt: bad parameters"); return WRT_ERR_INVALID;
@@ -460,10 +460,28 @@ int wrt_render_bdpt(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params*
     if (p->width <= 0 || p->height <= 0 || p->width != p->height) {
         set_error("wrt_render_bdpt: the film must be square and non-empty (bidirPathTracing.cpp:29-45)"); return WRT_ERR_INVALID;
     }
-    wrt_wavefront* wf = nullptr;
-    int rc = wavefront_get(sc, std::max(p->width * p->height * bdpt_batch(p), 1024), &wf);   // grow the pool first (frees the film)
-    if (rc) return rc;
     const size_t floats = (size_t)p->width * p->height * 3;
+    {
+        const int stride0 = p->iter_stride > 0 ? p->iter_stride : 1;
+        const int my_iters = p->iterations > p->iter_first ? (p->iterations - p->iter_first + stride0 - 1) / stride0 : 0;
+        if (sc->n_replicas > 0 && !sc->d_rng_tape && my_iters > 1 && !p->transpose_output) {
+            // several devices (wrt_init): iteration i of this call goes to device i mod N
+            auto fn = [&](wrt_scene* rs, int g, int n, float* d_film) -> int {
+                wrt_bdpt_params q = *p;
+                q.iter_first = p->iter_first + g * stride0;
+                q.iter_stride = stride0 * n;
+                q.film_scale = p->film_scale != 0.f ? p->film_scale : 1.f / (float)p->iterations;
+                return render_bdpt_device(rs, cam, &q, d_film, rs->stream);
+            };
+            float* film0 = nullptr;
+            int rcm = multi_render(sc, floats, my_iters, fn, &film0);
+            if (rcm) return rcm;
+            WRT_CUDA(cudaMemcpyAsync(film, film0, floats * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+            WRT_CUDA(cudaStreamSynchronize(sc->stream));
+            return WRT_OK;
+        }
+    }
+    int rc;
     float* d_film = nullptr;
     rc = wavefront_film(sc, floats * 2, &d_film);
     if (rc) return rc;

@@ -63,6 +63,7 @@ struct DevSceneView {  // passed to kernels by value
 
 #ifdef __CUDACC__
 #define WRT_MAX_TRACE_STREAMS 16
+#define WRT_MAX_DEVICES 16
 struct wrt_trace_ctx {               // per caller stream: work counter + traversal-stack scratch (trace_kernels.cu)
     cudaStream_t stream;
     unsigned long long* counter;
@@ -85,6 +86,10 @@ struct wrt_scene {
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev_fork;
     float* d_rng_tape; size_t rng_tape_floats; uint32_t rng_tape_stride;   // diagnostics: RNG replay (wrt_debug_set_rng_tape)
+    // multi-GPU (wrt_init): the primary scene (device 0 of the set) owns one replica per further device
+    struct wrt_scene* replica[WRT_MAX_DEVICES - 1]; int n_replicas;
+    bool peer_of_primary;            // (replicas) device 0 of the set can read this device's memory directly (NVLink / PCIe P2P)
+    float* d_film; size_t film_floats;   // library-owned device film of the host-buffer render calls
     struct wrt_wavefront* wf;        // lazily created integrator state (sub-pool 0; owns the film and BDPT buffers)
     struct wrt_wavefront* wf_extra[7]; // further PT sub-pools (each with its own stream), see pt_wavefront.cu
 };

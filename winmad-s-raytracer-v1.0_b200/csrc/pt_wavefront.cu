@@ -254,16 +254,16 @@ int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** ou
 
 int wavefront_get(wrt_scene* sc, int capacity, wrt_wavefront** out) { return wavefront_get_slot(sc, 0, capacity, out); }
 
+// The library-owned device film of the host-buffer entry points (owned by the scene, so growing a pool never frees it).
 int wavefront_film(wrt_scene* sc, size_t floats, float** out)
 {
-    wrt_wavefront* wf = sc->wf;
-    if (wf->film_floats < floats) {
-        if (wf->film) cudaFree(wf->film);
-        wf->film = nullptr; wf->film_floats = 0;
-        WRT_CUDA(cudaMalloc((void**)&wf->film, floats * sizeof(float)));
-        wf->film_floats = floats;
+    if (sc->film_floats < floats) {
+        if (sc->d_film) cudaFree(sc->d_film);
+        sc->d_film = nullptr; sc->film_floats = 0;
+        WRT_CUDA(cudaMalloc((void**)&sc->d_film, floats * sizeof(float)));
+        sc->film_floats = floats;
     }
-    *out = wf->film;
+    *out = sc->d_film;
     return WRT_OK;
 }
 
@@ -302,7 +302,7 @@ static void wavefront_free(wrt_wavefront* wf)
     cudaFree(wf->pool.hit_prim); cudaFree(wf->pool.hit_t);
     cudaFree(wf->queue[0]); cudaFree(wf->queue[1]);
     cudaFree(wf->shadow.a); cudaFree(wf->shadow.b); cudaFree(wf->shadow.c); cudaFree(wf->shadow.pixel);
-    cudaFree(wf->counters); if (wf->h_counters) cudaFreeHost(wf->h_counters); cudaFree(wf->film); cudaFree(wf->trav_scratch); cudaFree(wf->whitted);
+    cudaFree(wf->counters); if (wf->h_counters) cudaFreeHost(wf->h_counters); cudaFree(wf->trav_scratch); cudaFree(wf->whitted);
     for (int i = 0; i < wf->n_ev; i++) cudaEventDestroy(wf->ev[i]);
     delete[] wf->ev;
     if (wf->stream) cudaStreamDestroy(wf->stream);
@@ -404,8 +404,7 @@ static int whitted_pending(wrt_wavefront* wf, int levels, WhittedPending& out)
     return WRT_OK;
 }
 
-static int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st,
-                            bool whitted = false)
+int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st, bool whitted)
 {
     if (!cam) { set_error("wrt_render_pt: null camera"); return WRT_ERR_INVALID; }
     if (sc->view.n_lights <= 0) { set_error("wrt_render_pt: the scene has no light (the reference indexes an empty vector here)"); return WRT_ERR_INVALID; }
@@ -597,7 +596,7 @@ int wrt_render_pt_dev(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params*
     WRT_CUDA(cudaSetDevice(sc->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
     WRT_CUDA(cudaEventRecord(sc->ev0, st));
-    int rc = render_pt_device(sc, cam, p, d_film, st);
+    int rc = render_pt_device(sc, cam, p, d_film, st, false);
     if (rc) return rc;
     WRT_CUDA(cudaEventRecord(sc->ev1, st));
     WRT_CUDA(cudaStreamSynchronize(st));
@@ -649,11 +648,23 @@ static int render_pt_host(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_par
     PtParams P;
     int rc = pt_fill_params(p, P);
     if (rc) return rc;
-    wrt_wavefront* wf = nullptr;
-    {   // grow sub-pool 0 first: re-creating it frees the film it owns
-        PtPlan plan; pt_plan(P, plan, whitted);
-        rc = wavefront_get_slot(sc, 0, plan.cap[0], &wf);
+    if (sc->n_replicas > 0 && !sc->d_rng_tape && P.local_spp > 1) {
+        // several devices (wrt_init): sample i of this call (k = sample_first + i * stride) goes to device i mod N
+        const size_t floats = (size_t)p->width * p->height * 3;
+        const int stride0 = P.sample_stride;
+        auto fn = [&](wrt_scene* rs, int g, int n, float* d_film) -> int {
+            wrt_pt_params q = *p;
+            q.sample_first = P.sample_first + g * stride0;
+            q.sample_stride = stride0 * n;
+            q.film_scale = P.film_scale;                        // 1/spp of the WHOLE render, fused into every film_add
+            return render_pt_device(rs, cam, &q, d_film, rs->stream, whitted);
+        };
+        float* film0 = nullptr;
+        rc = multi_render(sc, floats, P.local_spp, fn, &film0);
         if (rc) return rc;
+        WRT_CUDA(cudaMemcpyAsync(film, film0, floats * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+        WRT_CUDA(cudaStreamSynchronize(sc->stream));
+        return WRT_OK;
     }
     const size_t floats = (size_t)p->width * p->height * 3;
     float* d_film = nullptr;

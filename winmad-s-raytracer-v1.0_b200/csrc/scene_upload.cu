@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "scene_layout.h"
+#include "wavefront.h"
 
 namespace wrt {
 
@@ -56,29 +57,15 @@ int wrt_set_device(int ordinal)
     return WRT_OK;
 }
 
-int wrt_scene_create(const wrt_scene_desc* d, wrt_scene** out)
+// Uploads a built layout to the CURRENT device.
+static int scene_create_on_current_device(SceneLayout& L, wrt_scene** out)
 {
-    if (!d || !out) { set_error("wrt_scene_create: null argument"); return WRT_ERR_INVALID; }
-    int ndev = 0;
-    {
-        cudaError_t e = cudaGetDeviceCount(&ndev);
-        if (e != cudaSuccess || ndev == 0) {
-            set_error("wrt_scene_create: no CUDA device (this library has no CPU path)");
-            return WRT_ERR_NO_DEVICE;
-        }
-    }
-    SceneLayout L;
-    std::string err;
-    if (!build_layout(d, L, err)) { set_error("wrt_scene_create: " + err); return WRT_ERR_INVALID; }
     std::vector<float4>& nodes = L.nodes; std::vector<float4>& recs = L.recs; std::vector<float4>& prims = L.prims;
     std::vector<DevMaterial>& mats = L.materials; std::vector<DevLight>& lights = L.lights;
-    const int64_t n_recs = L.n_recs;
-
-    // ---- upload --------------------------------------------------------------------------------
     wrt_scene* sc = new wrt_scene();
     memset(sc, 0, sizeof *sc);
     sc->traversal_mode = WRT_TRAVERSE_PRUNED;
-    sc->n_leaf_recs = n_recs;
+    sc->n_leaf_recs = L.n_recs;
     cudaGetDevice(&sc->device);
 #define UP(dst, vec, T_) do { \
         size_t bytes__ = std::max<size_t>((vec).size(), 1) * sizeof(T_); \
@@ -86,7 +73,7 @@ int wrt_scene_create(const wrt_scene_desc* d, wrt_scene** out)
         if (e__ == cudaSuccess && !(vec).empty()) e__ = cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof(T_), cudaMemcpyHostToDevice); \
         if (e__ != cudaSuccess) { int rc__ = cuda_fail(e__, "scene upload"); wrt_scene_destroy(sc); return rc__; } } while (0)
     {   // The root is node 0 and sibling pairs start at odd indices (breadth-first layout).  Placing node 0 at
-        // byte 32 of the allocation makes every child pair one aligned 64-byte read (pair_traverse.cuh).
+        // byte 32 of the allocation makes every child pair one aligned 64-byte read.
         const size_t bytes = (nodes.size() + 2) * sizeof(float4);
         cudaError_t e = cudaMalloc(&sc->d_nodes, bytes);
         if (e == cudaSuccess) e = cudaMemset(sc->d_nodes, 0, 2 * sizeof(float4));
@@ -116,26 +103,70 @@ int wrt_scene_create(const wrt_scene_desc* d, wrt_scene** out)
     return WRT_OK;
 }
 
+int wrt_scene_create(const wrt_scene_desc* d, wrt_scene** out)
+{
+    if (!d || !out) { set_error("wrt_scene_create: null argument"); return WRT_ERR_INVALID; }
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) {
+            set_error("wrt_scene_create: no CUDA device (this library has no CPU path)");
+            return WRT_ERR_NO_DEVICE;
+        }
+    }
+    SceneLayout L;
+    std::string err;
+    if (!build_layout(d, L, err)) { set_error("wrt_scene_create: " + err); return WRT_ERR_INVALID; }
+    const int n_multi = multi_device_count();
+    if (n_multi <= 1) {
+        if (n_multi == 1) WRT_CUDA(cudaSetDevice(multi_device(0)));
+        return scene_create_on_current_device(L, out);
+    }
+    // wrt_init named several devices: the primary scene on the first, one replica on each of the others
+    WRT_CUDA(cudaSetDevice(multi_device(0)));
+    wrt_scene* primary = nullptr;
+    int rc = scene_create_on_current_device(L, &primary);
+    if (rc) return rc;
+    for (int i = 1; i < n_multi; i++) {
+        cudaError_t e = cudaSetDevice(multi_device(i));
+        wrt_scene* r = nullptr;
+        rc = e == cudaSuccess ? scene_create_on_current_device(L, &r) : cuda_fail(e, "cudaSetDevice");
+        if (rc) { cudaSetDevice(multi_device(0)); wrt_scene_destroy(primary); return rc; }
+        r->peer_of_primary = multi_peer_of_primary(i);
+        primary->replica[primary->n_replicas++] = r;
+    }
+    WRT_CUDA(cudaSetDevice(multi_device(0)));
+    *out = primary;
+    return WRT_OK;
+}
+
 void wrt_scene_destroy(wrt_scene* sc)
 {
     if (!sc) return;
+    for (int i = 0; i < sc->n_replicas; i++) wrt_scene_destroy(sc->replica[i]);
+    sc->n_replicas = 0;
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    cudaSetDevice(sc->device);
     wavefront_destroy(sc);
     cudaFree(sc->d_nodes); cudaFree(sc->d_leaf_recs); cudaFree(sc->d_prims);
     cudaFree(sc->d_materials); cudaFree(sc->d_lights);
     cudaFree(sc->d_scratch_in); cudaFree(sc->d_scratch_out); cudaFree(sc->d_counters); cudaFree(sc->d_trav_scratch);
-    cudaFree(sc->d_rng_tape);
+    cudaFree(sc->d_rng_tape); cudaFree(sc->d_film);
     for (int i = 0; i < sc->n_trace_ctx; i++) { cudaFree(sc->trace_ctx[i].counter); cudaFree(sc->trace_ctx[i].scratch); }
     if (sc->stream) cudaStreamDestroy(sc->stream);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
     if (sc->ev_fork) cudaEventDestroy(sc->ev_fork);
     delete sc;
+    cudaSetDevice(prev_dev);
 }
 
 int wrt_scene_set_traversal(wrt_scene* sc, int mode)
 {
     if (!sc || (mode != WRT_TRAVERSE_EXACT && mode != WRT_TRAVERSE_PRUNED)) { set_error("bad traversal mode"); return WRT_ERR_INVALID; }
     sc->traversal_mode = mode;
+    for (int i = 0; i < sc->n_replicas; i++) sc->replica[i]->traversal_mode = mode;
     return WRT_OK;
 }
 
@@ -143,6 +174,7 @@ int wrt_scene_set_counting(wrt_scene* sc, int on)
 {
     if (!sc) { set_error("null scene"); return WRT_ERR_INVALID; }
     sc->counting = on == 2 ? 2 : (on ? 1 : 0);   // 1: EXACT (reference-semantics work), 2: PRUNED (this kernel's own work)
+    for (int i = 0; i < sc->n_replicas; i++) sc->replica[i]->counting = sc->counting;
     return WRT_OK;
 }
 

@@ -40,6 +40,9 @@ constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 #ifndef WRT_MIN_BLOCKS
 #define WRT_MIN_BLOCKS 9
 #endif
+#ifndef WRT_TOS_CACHE
+#define WRT_TOS_CACHE 1
+#endif
 
 struct PoolSmem {
     float4 a[kPoolRays];               // ox oy oz dx
@@ -175,9 +178,15 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 T.sp = spw & 0xffff;
                 T.degen = (spw >> 29) & 1;
                 bool need_pop = (spw >> 30) & 1;
-                int4 e = sm.e[slot];
-                T.res = e.x;
+                T.res = sm.e[slot].x;                             // (rec, rec_end, item are only touched when the ray leaves this ring)
+                int leaf_first = 0, leaf_end = 0;
                 float4* stk = gstack + slot;                      // entry (sp, slot) at stk[sp * kPoolRays]
+#if WRT_TOS_CACHE
+                // The newest stack entry stays in registers while the lane works on the ray: most pops follow their push within
+                // a step or two (near child skipped by its bounds / empty leaf), and then neither the store nor the dependent
+                // L2 load of the scratch stack happens.  T.sp counts the entries in the scratch stack only.
+                int tos_node = -1; float tos_t = 0.f, tos_tmax = 0.f;
+#endif
                 // (measured and dropped: unrolling this loop by 2 -1.4 %, fully -41 % (instruction cache); prefetch.global.L1
                 //  of the child pair right after the node header is known -19 % / -42 % for one / both children, of a
                 //  leaf's first records on leaf entry -4 %; a warp-uniform loop with a `live` flag instead of the breaks -4 %:
@@ -185,10 +194,16 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 for (int s = 0; s < kNodeSteps; s++) {
                     if (need_pop) {
                         need_pop = false;
-                        if (T.sp <= 0) { next = 2; break; }
-                        --T.sp;
-                        const float4 q = stk[(unsigned)T.sp * (unsigned)kPoolRays];
-                        T.node = __float_as_int(q.x); T.tmin = q.y; T.tmax = q.z;
+#if WRT_TOS_CACHE
+                        if (tos_node >= 0) { T.node = tos_node; T.tmin = tos_t; T.tmax = tos_tmax; tos_node = -1; }
+                        else
+#endif
+                        {
+                            if (T.sp <= 0) { next = 2; break; }
+                            --T.sp;
+                            const float4 q = stk[(unsigned)T.sp * (unsigned)kPoolRays];
+                            T.node = __float_as_int(q.x); T.tmin = q.y; T.tmax = q.z;
+                        }
                     }
                     if (r.tmax < T.tmin) { next = 2; break; }                              // KDtreeAccel.cpp:323
                     const float4* np = sc.nodes + 2 * (size_t)T.node;
@@ -202,7 +217,7 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                     const unsigned hi = packed >> 2;                  // child pair (interior) | record count (leaf)
                     const bool leaf = (packed & 3u) == WRT_LEAF_TAG;
                     if (skip || (leaf && hi == 0u)) { need_pop = true; continue; }
-                    if (leaf) { e.y = __float_as_int(na.x); e.z = e.y + (int)hi; next = 1; break; }
+                    if (leaf) { leaf_first = __float_as_int(na.x); leaf_end = leaf_first + (int)hi; next = 1; break; }
                     // interior step (trav_interior, KDtreeAccel.cpp:325-358) without branches; the push goes to the
                     // global scratch stack
                     const int axis = (int)(packed & 3u);
@@ -217,15 +232,25 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                     const bool near_only = (t > T.tmax) || (t <= 0.f);
                     const bool far_only = !near_only && (t < T.tmin);
                     const bool both = !near_only && !far_only;
+#if WRT_TOS_CACHE
+                    if (both) {
+                        if (tos_node >= 0 && T.sp < kPoolStack) { stk[(unsigned)T.sp * (unsigned)kPoolRays] = make_float4(__int_as_float(tos_node), tos_t, tos_tmax, 0.f); ++T.sp; }
+                        tos_node = far_n; tos_t = t; tos_tmax = T.tmax;
+                    }
+#else
                     if (both && T.sp < kPoolStack) { stk[(unsigned)T.sp * (unsigned)kPoolRays] = make_float4(__int_as_float(far_n), t, T.tmax, 0.f); ++T.sp; }
+#endif
                     T.node = far_only ? far_n : near_n;
                     T.tmax = both ? t : T.tmax;
                 }
                 if (next == 2) {
-                    src.done((size_t)(unsigned)e.w, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
+                    src.done((size_t)(unsigned)sm.e[slot].w, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
                 } else {
+#if WRT_TOS_CACHE
+                    if (tos_node >= 0 && T.sp < kPoolStack) { stk[(unsigned)T.sp * (unsigned)kPoolRays] = make_float4(__int_as_float(tos_node), tos_t, tos_tmax, 0.f); ++T.sp; }
+#endif
                     sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(T.node), __int_as_float(T.sp | (T.degen ? (1 << 29) : 0) | (need_pop ? (1 << 30) : 0)));
-                    if (next == 1) sm.e[slot] = e;
+                    if (next == 1) { sm.e[slot].y = leaf_first; sm.e[slot].z = leaf_end; }
                 }
             }
             const unsigned b0 = __ballot_sync(FULL, have && next == 0);

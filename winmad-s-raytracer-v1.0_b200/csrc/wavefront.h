@@ -60,7 +60,6 @@ struct wrt_wavefront {
     wrt::ShadowQueue shadow;
     unsigned long long* counters;       // device, WF_COUNTERS entries
     unsigned long long* h_counters;     // pinned host mirror
-    float* film; size_t film_floats;    // library-owned device film for host-buffer entry points
     void* bdpt;                         // BDPT-only buffers (bdpt_wavefront.cu)
     size_t bdpt_bytes;
     void* whitted; size_t whitted_bytes; // Whitted-only pending lists (pt_wavefront.cu)
@@ -71,7 +70,15 @@ struct wrt_wavefront {
     cudaEvent_t poll_ev[2];             // device-driven loops: marks the arrival of a batch's counter bank in h_counters
 };
 
+#include <functional>
 namespace wrt {
+// multi_gpu.cu
+int multi_device_count();
+int multi_device(int i);
+bool multi_peer_of_primary(int i);
+int multi_render(wrt_scene* sc, size_t floats, int n_units, const std::function<int(wrt_scene*, int, int, float*)>& fn, float** film0);
+int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st, bool whitted);
+int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* d_film, cudaStream_t st);
 int wavefront_get(wrt_scene* sc, int capacity, wrt_wavefront** out);
 int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** out);
 int wavefront_film(wrt_scene* sc, size_t floats, float** out);
