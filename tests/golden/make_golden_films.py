@@ -23,8 +23,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 CASES = {
     "cornell_pt": ("cornell", 64, "pt", 5, 1024, 16),          # 16 384 spp
     "small_mixed_pt": ("small_mixed", 64, "pt", 5, 4096, 16),  # 65 536 spp
-    "cornell_bdpt": ("cornell", 48, "bdpt", 0, 2048, 16),      # 32 768 iterations
-    "small_mixed_bdpt": ("small_mixed", 48, "bdpt", 0, 2048, 16),   # seeds 3000..: with seeds 1000.. one light-tracing vertex lands in the
+    "cornell_bdpt": ("cornell", 48, "bdpt", 0, 2048, 32),      # 65 536 iterations
+    "small_mixed_bdpt": ("small_mixed", 48, "bdpt", 0, 2048, 48),   # seeds 3000..: with seeds 1000.. one light-tracing vertex lands in the
                                                                      # camera plane and the reference aborts in Transform::tPoint's assert(wp != 0)
     "torus_pt": ("torus", 32, "pt", 7, 16384, 16),             # 262 144 spp: glass caustics, see the test's note
 }

@@ -116,7 +116,7 @@ def test_tape_too_short_is_refused(wrt):
 
 # ---- converged images against committed high-spp reference films ---------------------------------
 CONVERGED = {  # case -> device spp / iterations
-    "cornell_pt": 65536, "small_mixed_pt": 262144, "cornell_bdpt": 131072, "small_mixed_bdpt": 131072,
+    "cornell_pt": 65536, "small_mixed_pt": 262144, "cornell_bdpt": 262144, "small_mixed_bdpt": 262144,
 }
 
 
@@ -146,3 +146,23 @@ def test_converged_image_parity_per_pixel(wrt, case):
           "mean radiance %.5f vs %.5f" % (case, n, 2 * int(z["per_half"]), err, floor2, floor2 / 2, mine.mean(), refm.mean()))
     assert abs(mine.mean() - refm.mean()) <= 0.003 * refm.mean()
     assert err <= 0.01
+
+
+def test_torus_scene_converged_mean_radiance(wrt):
+    """torus.scene (BASELINE config 0's scene) at 262 144 spp from the reference, 32 x 32 pixels: the reference's OWN two halves
+    still differ by 7 % per pixel (light reaches the torus only through the glass cube, single-sample radiances reach 1e3 x the
+    mean), so a per-pixel bound is out of reach for the reference itself here; the per-pixel statement for this scene is the
+    RNG-tape test above (same random numbers, 99.9 % of the samples identical).  What converges is the mean radiance: 0.5 %."""
+    path = os.path.join(GOLDEN, "film_torus_pt.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden film not generated")
+    z = np.load(path)
+    res = int(z["res"])
+    sc = torus_small(res)
+    hs = util.host_scene(wrt, sc); scene = wrt.Scene(hs)
+    mine = scene.render_pt(hs.camera(), wrt.PtParams(res, res, 1048576, int(z["depth"]), 11, 0, 1, 0.0))
+    a, b = z["a"].astype(np.float64), z["b"].astype(np.float64)
+    refm = 0.5 * (a + b)
+    print("torus_pt: mean radiance %.6f (device, 1 048 576 spp) vs %.6f (reference, %d spp; halves %.6f / %.6f); per-pixel rRMSE %.4f, "
+          "reference two-half figure %.4f" % (mine.mean(), refm.mean(), 2 * int(z["per_half"]), a.mean(), b.mean(), util.rel_rmse(mine, refm), util.rel_rmse(a, b)))
+    assert abs(mine.mean() - refm.mean()) <= max(0.005 * refm.mean(), 1.5 * abs(a.mean() - b.mean()))

@@ -119,7 +119,10 @@ k_bdpt_light_shade(DevSceneView sc, BdptParams P, DevCamera cam, PathPool pool, 
     }
 }
 
-__global__ void __launch_bounds__(kBlock)
+#ifndef WRT_BDPT_CS_BLOCKS
+#define WRT_BDPT_CS_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(kBlock, WRT_BDPT_CS_BLOCKS)
 k_bdpt_camera_shade(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B, const uint32_t* __restrict__ queue_in,
                     uint32_t* __restrict__ queue_out, float* __restrict__ film, unsigned long long* ctr, int parity)
 {
@@ -355,7 +358,7 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
     const int g_di_p = persistent_grid_for((const void*)k_bdpt_di<true>, kBlock);
     const int g_di_e = persistent_grid_for((const void*)k_bdpt_di<false>, kBlock);
 
-    rc = wavefront_events(wf, 4 * 64);
+    rc = wavefront_events(wf, kEvPerIter * 64);
     if (rc) return rc;
     const int kMaxTimed = 4096;
     int timed = 0;
@@ -380,8 +383,8 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
             for (int it = 0; it < phase_iters; it++, iter++) {
                 const int par = iter & 1;
                 const bool time_it = timed < kMaxTimed;
-                if (time_it && 4 * (timed + 1) > wf->n_ev) { rc = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (rc) return rc; }
-                cudaEvent_t* ev = time_it ? &wf->ev[4 * timed] : nullptr;
+                if (time_it && kEvPerIter * (timed + 1) > wf->n_ev) { rc = wavefront_events(wf, std::min(kEvPerIter * kMaxTimed, wf->n_ev * 2)); if (rc) return rc; }
+                cudaEvent_t* ev = time_it ? &wf->ev[kEvPerIter * timed] : nullptr;
                 WRT_CUDA(cudaMemsetAsync(wf->counters + par * WF_BANK, 0, WF_BANK * sizeof(unsigned long long), st));
                 if (ev) cudaEventRecord(ev[0], st);
                 if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, 0);
@@ -393,7 +396,7 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
                     k_bdpt_light_shade<<<g_ls, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, Bv, wf->queue[cur], wf->queue[cur ^ 1], wf->counters, par);
                 else
                     k_bdpt_camera_shade<<<g_cs, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[cur], wf->queue[cur ^ 1], d_film, wf->counters, par);
-                if (ev) cudaEventRecord(ev[2], st);
+                if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
                 if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par);
                 else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par);
                 else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch);
@@ -402,7 +405,7 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
                     if (pruned) k_bdpt_di<true><<<g_di_p, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters, par);
                     else k_bdpt_di<false><<<g_di_e, kBlock, 0, st>>>(sc->view, Bv.di, d_film, P.film_scale, wf->counters, par);
                 }
-                if (ev) { cudaEventRecord(ev[3], st); timed++; }
+                if (ev) { cudaEventRecord(ev[4], st); timed++; }
                 WRT_CUDA(cudaGetLastError());
                 sc->stats.kernel_launches += 3 + (phase == 1 ? 1 : 0);
                 cur ^= 1;

@@ -223,10 +223,20 @@ static int wavefront_alloc(wrt_wavefront* wf, int capacity)
     WRT_CUDA(cudaMalloc((void**)&wf->shadow.b, P * sizeof(float4)));
     WRT_CUDA(cudaMalloc((void**)&wf->shadow.c, P * sizeof(float4)));
     WRT_CUDA(cudaMalloc((void**)&wf->shadow.pixel, P * sizeof(uint32_t)));
+    WRT_CUDA(cudaMalloc((void**)&wf->shadow2.a, P * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&wf->shadow2.b, P * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&wf->shadow2.c, P * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&wf->shadow2.pixel, P * sizeof(uint32_t)));
     WRT_CUDA(cudaMalloc((void**)&wf->counters, WF_COUNTERS * sizeof(unsigned long long)));
     WRT_CUDA(cudaMallocHost((void**)&wf->h_counters, WF_COUNTERS * sizeof(unsigned long long)));
     WRT_CUDA(cudaStreamCreateWithFlags(&wf->stream, cudaStreamNonBlocking));
     { int rc = ensure_trav_scratch(&wf->trav_scratch, &wf->trav_scratch_bytes); if (rc) return rc; }
+    { int rc = ensure_trav_scratch(&wf->trav_scratch2, &wf->trav_scratch2_bytes); if (rc) return rc; }
+    WRT_CUDA(cudaStreamCreateWithFlags(&wf->shadow_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        WRT_CUDA(cudaEventCreateWithFlags(&wf->shaded_ev[i], cudaEventDisableTiming));
+        WRT_CUDA(cudaEventCreateWithFlags(&wf->shadowed_ev[i], cudaEventDisableTiming));
+    }
     WRT_CUDA(cudaEventCreateWithFlags(&wf->join_ev, cudaEventDisableTiming));
     WRT_CUDA(cudaEventCreateWithFlags(&wf->poll_ev[0], cudaEventDisableTiming));
     WRT_CUDA(cudaEventCreateWithFlags(&wf->poll_ev[1], cudaEventDisableTiming));
@@ -280,15 +290,15 @@ int wavefront_events(wrt_wavefront* wf, int n)
     return WRT_OK;
 }
 
-// Events are recorded as e[4i] (before extend) e[4i+1] (before shade) e[4i+2] (before shadow) e[4i+3] (after).
+// Events per iteration (kEvPerIter = 5): [0] before extend, [1] after extend, [2] after shade, [3] before shadow, [4] after shadow.
 void wavefront_sum_stage_times(wrt_scene* sc, wrt_wavefront* wf, int iters_timed)
 {
     double ext = 0, shd = 0, shw = 0;
     for (int i = 0; i < iters_timed; i++) {
         float a = 0, b = 0, c = 0;
-        cudaEventElapsedTime(&a, wf->ev[4 * i], wf->ev[4 * i + 1]);
-        cudaEventElapsedTime(&b, wf->ev[4 * i + 1], wf->ev[4 * i + 2]);
-        cudaEventElapsedTime(&c, wf->ev[4 * i + 2], wf->ev[4 * i + 3]);
+        cudaEventElapsedTime(&a, wf->ev[kEvPerIter * i], wf->ev[kEvPerIter * i + 1]);
+        cudaEventElapsedTime(&b, wf->ev[kEvPerIter * i + 1], wf->ev[kEvPerIter * i + 2]);
+        cudaEventElapsedTime(&c, wf->ev[kEvPerIter * i + 3], wf->ev[kEvPerIter * i + 4]);
         ext += a; shd += b; shw += c;
     }
     sc->stats.extend_ms = ext; sc->stats.shade_ms = shd; sc->stats.shadow_ms = shw;
@@ -302,6 +312,9 @@ static void wavefront_free(wrt_wavefront* wf)
     cudaFree(wf->pool.hit_prim); cudaFree(wf->pool.hit_t);
     cudaFree(wf->queue[0]); cudaFree(wf->queue[1]);
     cudaFree(wf->shadow.a); cudaFree(wf->shadow.b); cudaFree(wf->shadow.c); cudaFree(wf->shadow.pixel);
+    cudaFree(wf->shadow2.a); cudaFree(wf->shadow2.b); cudaFree(wf->shadow2.c); cudaFree(wf->shadow2.pixel); cudaFree(wf->trav_scratch2);
+    if (wf->shadow_stream) cudaStreamDestroy(wf->shadow_stream);
+    for (int i = 0; i < 2; i++) { if (wf->shaded_ev[i]) cudaEventDestroy(wf->shaded_ev[i]); if (wf->shadowed_ev[i]) cudaEventDestroy(wf->shadowed_ev[i]); }
     cudaFree(wf->counters); if (wf->h_counters) cudaFreeHost(wf->h_counters); cudaFree(wf->trav_scratch); cudaFree(wf->whitted);
     for (int i = 0; i < wf->n_ev; i++) cudaEventDestroy(wf->ev[i]);
     delete[] wf->ev;
@@ -372,8 +385,24 @@ static void pt_plan(const PtParams& P, PtPlan& plan, bool whitted = false)
     int k = sub_pools();
     if (total < (1ull << 18)) k = 1;
     plan.k = k;
-    const unsigned long long per = (total + k - 1) / k;
-    for (int j = 0; j < k; j++) plan.cap[j] = (int)std::max<unsigned long long>(per, 1024ull);
+    // Sub-pool sizes.  When the pool holds the whole frame (no slot is ever regenerated: a frame of <= 2^26 samples, e.g. one
+    // GPU's share of a sharded render) every sub-pool runs the same short chain of iterations — one large launch of camera
+    // rays, then a handful of small, latency-bound ones — and equal sub-pools would walk through it in lock-step, their
+    // tails coinciding.  Unequal shares (WRT_SUBPOOL_WEIGHTS, default 65,35 for two) stagger the chains, so one sub-pool's
+    // small iterations run beside the other's large one.  With regeneration the queues stay full and equal shares are used.
+    double wgt[8]; double sum = 0;
+    const bool staggers = P.total_samples <= total;
+    for (int j = 0; j < k; j++) wgt[j] = 1.0;
+    if (staggers && k == 2) { wgt[0] = 65; wgt[1] = 35; }
+    if (const char* e = getenv("WRT_SUBPOOL_WEIGHTS")) {
+        int j = 0; const char* q = e;
+        while (*q && j < k) { wgt[j++] = std::max(1.0, atof(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
+    }
+    for (int j = 0; j < k; j++) sum += wgt[j];
+    for (int j = 0; j < k; j++) {
+        const unsigned long long share = (unsigned long long)std::ceil((double)total * wgt[j] / sum);
+        plan.cap[j] = (int)std::max<unsigned long long>(std::min<unsigned long long>(share, 1ull << 27), 1024ull);
+    }
 }
 
 // Host-side view of one sub-pool's device-driven loop.  Iterations are enqueued in batches; after every batch the bank
@@ -435,7 +464,7 @@ int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* 
     for (int j = 0; j < plan.k; j++) {
         rc = wavefront_get_slot(sc, j, plan.cap[j], &sub[j].wf);
         if (rc) return rc;
-        rc = wavefront_events(sub[j].wf, 4 * 64);
+        rc = wavefront_events(sub[j].wf, kEvPerIter * 64);
         if (rc) return rc;
         if (whitted) { rc = whitted_pending(sub[j].wf, wh_levels, wh_pend[j]); if (rc) return rc; }
     }
@@ -474,6 +503,7 @@ int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* 
     for (int j = 0; j < plan.k; j++) WRT_CUDA(cudaStreamWaitEvent(sub[j].wf->stream, sc->ev_fork, 0));
 
     const int kMaxTimed = 2048;
+    const bool shadow_on_own_stream = !(getenv("WRT_SHADOW_STREAM") && atoi(getenv("WRT_SHADOW_STREAM")) == 0);   // A/B knob
     const bool regenerates = P.total_samples > first;       // some slot will take a second camera sample
     // Without regeneration a path slot lives for at most max_depth + 1 vertices (+ the emitter hit that ends it): the number
     // of iterations is known up front and nothing has to be read back at all.
@@ -486,8 +516,12 @@ int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* 
         const int par = s.iter & 1, cur = s.iter & 1;           // queue[cur] is consumed, queue[cur ^ 1] produced
         const size_t cap = (size_t)wf->capacity;
         const bool time_it = s.timed < kMaxTimed;
-        if (time_it && 4 * (s.timed + 1) > wf->n_ev) { int r = wavefront_events(wf, std::min(4 * kMaxTimed, wf->n_ev * 2)); if (r) return r; }
-        cudaEvent_t* ev = time_it ? &wf->ev[4 * s.timed] : nullptr;
+        if (time_it && kEvPerIter * (s.timed + 1) > wf->n_ev) { int r = wavefront_events(wf, std::min(kEvPerIter * kMaxTimed, wf->n_ev * 2)); if (r) return r; }
+        cudaEvent_t* ev = time_it ? &wf->ev[kEvPerIter * s.timed] : nullptr;
+        cudaStream_t qs = shadow_on_own_stream ? wf->shadow_stream : q;
+        const ShadowQueue& sq = par ? wf->shadow2 : wf->shadow;
+        // bank `par` and shadow queue `par` were last used by iteration iter - 2, whose shadow kernel may still be running
+        if (s.iter >= 2) WRT_CUDA(cudaStreamWaitEvent(q, wf->shadowed_ev[par], 0));
         WRT_CUDA(cudaMemsetAsync(wf->counters + par * WF_BANK, 0, WF_BANK * sizeof(unsigned long long), q));
         if (ev) cudaEventRecord(ev[0], q);
         if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, cap);
@@ -495,16 +529,21 @@ int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* 
         else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, cap);
         else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, cap);
         if (ev) cudaEventRecord(ev[1], q);
-        if (whitted) k_wh_shade<<<g_wshade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], wf->queue[cur ^ 1], wf->shadow,
+        if (whitted) k_wh_shade<<<g_wshade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], wf->queue[cur ^ 1], sq,
                                                             d_film, wf->counters, par, next_sample, cap, wh_pend[s.index], wh_levels);
-        else k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], wf->queue[cur ^ 1], wf->shadow,
+        else k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], wf->queue[cur ^ 1], sq,
                                                    d_film, wf->counters, par, next_sample, cap);
         if (ev) cudaEventRecord(ev[2], q);
-        if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, par);
-        else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, par);
-        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch);
-        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, q>>>(sc->view, wf->shadow, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch);
-        if (ev) { cudaEventRecord(ev[3], q); s.timed++; }
+        WRT_CUDA(cudaEventRecord(wf->shaded_ev[par], q));
+        // the shadow kernel: its own stream, overlapping the next iteration's extend + shade
+        WRT_CUDA(cudaStreamWaitEvent(qs, wf->shaded_ev[par], 0));
+        if (ev) cudaEventRecord(ev[3], qs);
+        if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, qs>>>(sc->view, sq, d_film, P.film_scale, wf->counters, par);
+        else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, qs>>>(sc->view, sq, d_film, P.film_scale, wf->counters, par);
+        else if (pruned) k_pt_shadow<true><<<g_sh_p, kBlock, 0, qs>>>(sc->view, sq, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch2);
+        else k_pt_shadow<false><<<g_sh_e, kBlock, 0, qs>>>(sc->view, sq, d_film, P.film_scale, wf->counters, par, (float4*)wf->trav_scratch2);
+        if (ev) { cudaEventRecord(ev[4], qs); s.timed++; }
+        WRT_CUDA(cudaEventRecord(wf->shadowed_ev[par], qs));
         WRT_CUDA(cudaGetLastError());
         sc->stats.kernel_launches += 3;
         s.iter++;
@@ -551,8 +590,9 @@ int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* 
             if (++guard > (1ull << 32)) { set_error("wrt_render_pt: runaway iteration count"); return WRT_ERR_CUDA; }
         }
     }
-    // join: the caller's stream continues after every sub-pool stream
+    // join: the caller's stream continues after every sub-pool stream (and its shadow stream)
     for (int j = 0; j < plan.k; j++) {
+        for (int par = 0; par < 2; par++) if (sub[j].iter > par) WRT_CUDA(cudaStreamWaitEvent(sub[j].wf->stream, sub[j].wf->shadowed_ev[par], 0));
         WRT_CUDA(cudaEventRecord(sub[j].wf->join_ev, sub[j].wf->stream));
         WRT_CUDA(cudaStreamWaitEvent(st, sub[j].wf->join_ev, 0));
     }

@@ -40,8 +40,15 @@ constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 #ifndef WRT_MIN_BLOCKS
 #define WRT_MIN_BLOCKS 9
 #endif
-#ifndef WRT_TOS_CACHE
-#define WRT_TOS_CACHE 1
+// Tail of a launch: once the global work counter is exhausted and a warp is down to its last rays, those are the rays that
+// decide when the launch ends — and on the scenes here they are long because of LEAF work (torus.scene: mean 20, p99.9 1300,
+// max 1500 primitive tests per ray).  With at most WRT_COOP_RAYS rays waiting for primitive tests the warp stops giving one lane
+// to one ray and tests 32 records of ONE ray per pass instead (coop_leaf below).
+#ifndef WRT_COOP_RAYS
+#define WRT_COOP_RAYS 4
+#endif
+#ifndef WRT_COOP_MIN_RECORDS
+#define WRT_COOP_MIN_RECORDS 8
 #endif
 
 struct PoolSmem {
@@ -55,23 +62,80 @@ struct PoolSmem {
 
 constexpr size_t kPoolStackBytesPerWarp = (size_t)kPoolStack * kPoolRays * sizeof(float4);
 
-template <bool PRUNED, class Src>
-__device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n,
-                                             PoolSmem& sm, float4* __restrict__ gstack)
+// One cooperative pass over the rest of a ray's leaf (see WRT_COOP_RAYS); only the tail loop (pooled_tail, out of line) calls it.
+// Returns true when the query was decided and consumed (boolean queries); otherwise the ray goes back to the node ring.
+template <class Src>
+__device__ __forceinline__ bool coop_leaf(const DevSceneView& sc, Src& src, PoolSmem& sm, unsigned slot, unsigned lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    const float4 a = sm.a[slot], b = sm.b[slot];
+    RayIn r; r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
+    const int4 e = sm.e[slot];
+    float best = sm.c[slot].w;
+    int res = e.x;
+    bool decided = false;
+    for (int base = e.y; base < e.z && !decided; base += 32) {
+        const int my = base + (int)lane;
+        bool hit = false; float t = 0.f; int prim = -1;
+        if (my < e.z) {
+            const float4* rec = sc.leaf_recs + 3 * (size_t)my;
+            const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+            const int kind = __float_as_int(r2.w);
+            if (kind == 0) hit = triangle_t(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, t);
+            else if (kind == 1) {
+                const float lo[3] = { r1.y, r1.z, r1.w }, hi[3] = { r2.x, r2.y, r2.z };
+                int inside;
+                hit = sphere_t(r0.x, r0.y, r0.z, r1.x, lo, hi, r, t, inside);
+            }
+            prim = __float_as_int(r0.w);
+        }
+        unsigned m = __ballot_sync(FULL, hit);
+        const float best0 = best;
+        while (m) {
+            const int i = __ffs(m) - 1;
+            m &= m - 1u;
+            const float ti = __shfl_sync(FULL, t, i);
+            const int pi = __shfl_sync(FULL, prim, i);
+            if (ti - best < -WRT_EPS) { best = ti; res = pi; }
+        }
+        if (Src::kCanDecide && best < best0) {
+            float tx, ty, tz;
+            src.target((size_t)(unsigned)e.w, tx, ty, tz);
+            decided = occlusion_decided(r, best, tx, ty, tz);
+        }
+    }
+    if (lane == 0) {
+        if (decided) src.done((size_t)(unsigned)e.w, r, res, best);
+        else {
+            sm.c[slot].w = best;
+            sm.e[slot].x = res; sm.e[slot].y = e.z;
+            sm.d[slot].w = __int_as_float(__float_as_int(sm.d[slot].w) | (1 << 30));     // need_pop
+        }
+    }
+    return decided;
+}
+
+struct PoolRings { unsigned hn, tn, hp, tp, hf, tf; };     // ring heads / tails (monotonic), warp-uniform
+
+// The scheduler loop.  TAIL = false: the steady state described at the top of this file; it returns as soon as the global
+// work counter is exhausted and at most WRT_COOP_RAYS rays are left in the pool.  TAIL = true: finishes those last rays —
+// same node rounds, but rays waiting for primitive tests get the cooperative leaf pass (coop_leaf).  Two instantiations, so
+// that the tail's code and registers stay out of the steady-state loop.
+template <bool PRUNED, bool TAIL, class Src>
+__device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n,
+                                            PoolSmem& sm, float4* __restrict__ gstack, PoolRings& R)
 {
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned RM = kPoolRays - 1;
-    unsigned hn = 0, tn = 0, hp = 0, tp = 0, hf = 0, tf = kPoolRays;   // ring heads / tails (monotonic)
-    for (unsigned i = lane; i < (unsigned)kPoolRays; i += 32) sm.ring[2][i] = (unsigned char)i;
-    __syncwarp();
-    bool exhausted = false;
+    unsigned hn = R.hn, tn = R.tn, hp = R.hp, tp = R.tp, hf = R.hf, tf = R.tf;
+    bool exhausted = TAIL;
 
     for (;;) {
         // ---- refill free slots from the global work counter ------------------------------------
         unsigned nfree = tf - hf;
-        if (!exhausted && nfree >= kMinRefill) {
+        if (!TAIL && !exhausted && nfree >= kMinRefill) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(counter, (unsigned long long)nfree);
             base = __shfl_sync(FULL, base, 0);
@@ -111,6 +175,23 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
         const unsigned cn = tn - hn, cp = tp - hp;
         if (cn + cp == 0) {
             if (exhausted) break;
+            continue;
+        }
+        if (!TAIL && WRT_COOP_RAYS > 0 && exhausted && cn + cp <= (unsigned)WRT_COOP_RAYS) break;     // the tail loop takes over
+        // (a ray with a short rest of a leaf is served as well by the ordinary primitive round, which takes all waiting rays at once)
+        if (TAIL && cp > 0 && (cp == 1u || sm.e[sm.ring[1][hp & RM]].z - sm.e[sm.ring[1][hp & RM]].y >= WRT_COOP_MIN_RECORDS)) {
+            // ---- cooperative leaf pass (tail of the launch): the whole warp works on the FIRST ray of the prim ring --------
+            // Lane l tests record rec + l of the ray's leaf (Triangle::hit / Sphere::hit with their exact arithmetic, skip records
+            // are no-ops: every primitive of the leaf is tested, as the reference does), then the hits are offered to the
+            // acceptance rule `t - best < -EPS` in RECORD ORDER (KDtreeAccel.cpp:363-373) — the same fold the sequential loop
+            // performs, so res / best come out identical.
+            const unsigned slot = sm.ring[1][hp & RM];
+            hp += 1;
+            __syncwarp();
+            const bool decided = coop_leaf(sc, src, sm, slot, lane);
+            if (lane == 0) sm.ring[decided ? 2 : 0][(decided ? tf : tn) & RM] = (unsigned char)slot;
+            if (decided) tf += 1; else tn += 1;
+            __syncwarp();
             continue;
         }
         if (cp >= cn) {
@@ -181,12 +262,6 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 T.res = sm.e[slot].x;                             // (rec, rec_end, item are only touched when the ray leaves this ring)
                 int leaf_first = 0, leaf_end = 0;
                 float4* stk = gstack + slot;                      // entry (sp, slot) at stk[sp * kPoolRays]
-#if WRT_TOS_CACHE
-                // The newest stack entry stays in registers while the lane works on the ray: most pops follow their push within
-                // a step or two (near child skipped by its bounds / empty leaf), and then neither the store nor the dependent
-                // L2 load of the scratch stack happens.  T.sp counts the entries in the scratch stack only.
-                int tos_node = -1; float tos_t = 0.f, tos_tmax = 0.f;
-#endif
                 // (measured and dropped: unrolling this loop by 2 -1.4 %, fully -41 % (instruction cache); prefetch.global.L1
                 //  of the child pair right after the node header is known -19 % / -42 % for one / both children, of a
                 //  leaf's first records on leaf entry -4 %; a warp-uniform loop with a `live` flag instead of the breaks -4 %:
@@ -194,16 +269,10 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                 for (int s = 0; s < kNodeSteps; s++) {
                     if (need_pop) {
                         need_pop = false;
-#if WRT_TOS_CACHE
-                        if (tos_node >= 0) { T.node = tos_node; T.tmin = tos_t; T.tmax = tos_tmax; tos_node = -1; }
-                        else
-#endif
-                        {
-                            if (T.sp <= 0) { next = 2; break; }
-                            --T.sp;
-                            const float4 q = stk[(unsigned)T.sp * (unsigned)kPoolRays];
-                            T.node = __float_as_int(q.x); T.tmin = q.y; T.tmax = q.z;
-                        }
+                        if (T.sp <= 0) { next = 2; break; }
+                        --T.sp;
+                        const float4 q = stk[(unsigned)T.sp * (unsigned)kPoolRays];
+                        T.node = __float_as_int(q.x); T.tmin = q.y; T.tmax = q.z;
                     }
                     if (r.tmax < T.tmin) { next = 2; break; }                              // KDtreeAccel.cpp:323
                     const float4* np = sc.nodes + 2 * (size_t)T.node;
@@ -232,23 +301,13 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
                     const bool near_only = (t > T.tmax) || (t <= 0.f);
                     const bool far_only = !near_only && (t < T.tmin);
                     const bool both = !near_only && !far_only;
-#if WRT_TOS_CACHE
-                    if (both) {
-                        if (tos_node >= 0 && T.sp < kPoolStack) { stk[(unsigned)T.sp * (unsigned)kPoolRays] = make_float4(__int_as_float(tos_node), tos_t, tos_tmax, 0.f); ++T.sp; }
-                        tos_node = far_n; tos_t = t; tos_tmax = T.tmax;
-                    }
-#else
                     if (both && T.sp < kPoolStack) { stk[(unsigned)T.sp * (unsigned)kPoolRays] = make_float4(__int_as_float(far_n), t, T.tmax, 0.f); ++T.sp; }
-#endif
                     T.node = far_only ? far_n : near_n;
                     T.tmax = both ? t : T.tmax;
                 }
                 if (next == 2) {
                     src.done((size_t)(unsigned)sm.e[slot].w, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
                 } else {
-#if WRT_TOS_CACHE
-                    if (tos_node >= 0 && T.sp < kPoolStack) { stk[(unsigned)T.sp * (unsigned)kPoolRays] = make_float4(__int_as_float(tos_node), tos_t, tos_tmax, 0.f); ++T.sp; }
-#endif
                     sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(T.node), __int_as_float(T.sp | (T.degen ? (1 << 29) : 0) | (need_pop ? (1 << 30) : 0)));
                     if (next == 1) { sm.e[slot].y = leaf_first; sm.e[slot].z = leaf_end; }
                 }
@@ -265,6 +324,28 @@ __device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, u
             __syncwarp();
         }
     }
+    R.hn = hn; R.tn = tn; R.hp = hp; R.tp = tp; R.hf = hf; R.tf = tf;
+}
+
+template <bool PRUNED, class Src>
+#if !defined(WRT_WARPSIM)
+__device__ __noinline__
+#endif
+void pooled_tail(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n, PoolSmem& sm, float4* __restrict__ gstack, PoolRings& R)
+{
+    pooled_loop<PRUNED, true>(sc, src, counter, n, sm, gstack, R);
+}
+
+template <bool PRUNED, class Src>
+__device__ __forceinline__ void trace_pooled(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n,
+                                             PoolSmem& sm, float4* __restrict__ gstack)
+{
+    const unsigned lane = threadIdx.x & 31;
+    PoolRings R = { 0u, 0u, 0u, 0u, 0u, (unsigned)kPoolRays };
+    for (unsigned i = lane; i < (unsigned)kPoolRays; i += 32) sm.ring[2][i] = (unsigned char)i;
+    __syncwarp();
+    pooled_loop<PRUNED, false>(sc, src, counter, n, sm, gstack, R);
+    if ((R.tn - R.hn) + (R.tp - R.hp) != 0u) pooled_tail<PRUNED>(sc, src, counter, n, sm, gstack, R);
 }
 
 // Compile-time choice of the scheduler used by the kernels (A/B measured in profiles/):

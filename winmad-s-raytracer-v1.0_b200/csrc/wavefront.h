@@ -68,6 +68,13 @@ struct wrt_wavefront {
     cudaStream_t stream;                // this sub-pool's own stream (PT runs sub-pools concurrently)
     cudaEvent_t join_ev;
     cudaEvent_t poll_ev[2];             // device-driven loops: marks the arrival of a batch's counter bank in h_counters
+    // PT: the shadow kernel of iteration i runs on its own stream, next to extend / shade of iteration i + 1 (it only adds
+    // to the film), so an iteration's critical path is extend -> shade.  Needs a second shadow queue (iteration parity), a
+    // second traversal scratch and two events per parity.
+    wrt::ShadowQueue shadow2;
+    void* trav_scratch2; size_t trav_scratch2_bytes;
+    cudaStream_t shadow_stream;
+    cudaEvent_t shaded_ev[2], shadowed_ev[2];
 };
 
 #include <functional>
@@ -85,5 +92,6 @@ int wavefront_film(wrt_scene* sc, size_t floats, float** out);
 int persistent_grid_for(const void* kernel, int block);
 int wavefront_events(wrt_wavefront* wf, int n);
 void wavefront_sum_stage_times(wrt_scene* sc, wrt_wavefront* wf, int iters_timed);
+constexpr int kEvPerIter = 5;   // [0] before extend [1] after extend [2] after shade [3] before shadow [4] after shadow
 }
 #endif
