@@ -275,7 +275,7 @@ void hs_render_bdpt(void* hv, const wrt_camera* cam, const wrt_bdpt_params* p, i
             for (;;) {
                 float t; int prim = trace(ray, t);
                 V3 hit, emit_c; Bsdf bsdf; bool emit, has_di; DiEntry di;
-                int k = bdpt_camera_pre(sc, P, ray, st, prim, t, hit, bsdf, emit, emit_c, has_di, di);
+                V3 nrm; int k = bdpt_camera_pre(sc, P, ray, st, prim, t, hit, nrm, bsdf, emit, emit_c, has_di, di);
                 if (emit) add(st.index, emit_c);
                 if (k == 0) break;
                 if (has_di && visible(di.q)) {

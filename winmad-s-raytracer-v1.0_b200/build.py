@@ -85,9 +85,10 @@ def build_warpsim(force=False):
     src = os.path.join(ROOT, "tests", "hostsim", "warpsim.cpp")
     out = os.path.join(ROOT, "tests", "hostsim", "libwrt_warpsim.so")
     deps = [src, os.path.join(HERE, "csrc/scene_layout.cpp")] + [os.path.join(HERE, h) for h in HEADERS]
-    if force or _newer(out, deps):
+    extra = os.environ.get("WRT_WARPSIM_DEFS", "").split()      # e.g. -DWRT_STACK8=0 to test a non-default scheduler variant
+    if force or extra or _newer(out, deps):
         _run([CXX, "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-Wall", "-Wno-unknown-pragmas",
-              "-Wno-unused-function", "-Wno-unused-variable", "-DWRT_HOSTSIM", "-DWRT_WARPSIM", "-I", os.path.join(HERE, "csrc"),
+              "-Wno-unused-function", "-Wno-unused-variable", "-DWRT_HOSTSIM", "-DWRT_WARPSIM"] + extra + ["-I", os.path.join(HERE, "csrc"),
               "-o", out, src, os.path.join(HERE, "csrc/scene_layout.cpp"), "-lpthread"])
     return out
 

@@ -303,13 +303,14 @@ WRT_HD bool bdpt_direct_illumination(const DevSceneView& sc, const Bsdf& bsdf, V
 // Head of one camera-path vertex (:150-217).  Returns 0 = path ends, 1 = continue and connect to the
 // light vertices (non-delta BSDF), 2 = continue without connections (delta BSDF).
 WRT_HD int bdpt_camera_pre(const DevSceneView& sc, const BdptParams& P, const RayIn& ray, BdptPath& st, int prim, float t,
-                           V3& hit, Bsdf& bsdf, bool& emit, V3& emit_c, bool& has_di, DiEntry& di)
+                           V3& hit, V3& nrm, Bsdf& bsdf, bool& emit, V3& emit_c, bool& has_di, DiEntry& di)
 {
     emit = false; has_di = false;
     if (prim < 0) return 0;
     HitInfo h;
     fill_hit(sc, prim, ray, t, h);
     hit = v3(h.px, h.py, h.pz);
+    nrm = v3(h.nx, h.ny, h.nz);      // the normal the BSDF was built from (the connection kernel rebuilds the BSDF from it)
     const V3 rdir = v3(ray.dx, ray.dy, ray.dz);
     bsdf_init(bsdf, -rdir, v3(h.nx, h.ny, h.nz), h.matid, sc);
     if (bsdf.mat_id == 0) return 0;

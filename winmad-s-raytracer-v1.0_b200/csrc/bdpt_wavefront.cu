@@ -25,6 +25,7 @@ struct BdptBuffers {
     int* nverts;             // [n_paths]
     ShadowQueue conn; size_t conn_cap;
     float4* di; size_t di_cap;   // 6 float4 per entry
+    float4* cverts;          // [5][n_paths] camera-vertex records of the current iteration (k_bdpt_connect)
 };
 
 __device__ __forceinline__ void bdpt_store(const PathPool& pool, float* dvc, uint32_t slot, const RayIn& r, const BdptPath& st)
@@ -119,10 +120,18 @@ k_bdpt_light_shade(DevSceneView sc, BdptParams P, DevCamera cam, PathPool pool, 
     }
 }
 
-#ifndef WRT_BDPT_CS_BLOCKS
-#define WRT_BDPT_CS_BLOCKS 1
-#endif
-__global__ void __launch_bounds__(kBlock, WRT_BDPT_CS_BLOCKS)
+// Camera-path vertex, split in two kernels (round 2; the single kernel held the path state, its BSDF, the direct-illumination
+// entry AND a loop over the stored light vertices live at once: 168 registers, 12 resident warps per SM, 13.5 of 32 lanes
+// busy — profiles/r2_ncu_bdpt_camera_shade_before.md):
+//   k_bdpt_camera_shade  one thread per path: hit, emission, direct-illumination entry, the record the connections need
+//                        (position, throughput, dVCM / dVC, wi, normal, material, length — everything connectVertices reads of the
+//                        camera state, bidirPathTracing.cpp:611-665; the BSDF is rebuilt from (wi, n, material) exactly as it is for
+//                        the stored light vertices), then sampleScattering;
+//   k_bdpt_connect       one thread per (camera vertex, light vertex) pair.
+// The reference walks the light vertices of a pixel in order and `break`s at the first one with
+// lv.length + 1 + camera.length > maxPathLength (:238-240); stored lengths increase strictly along a light path, so the
+// per-pair test `> max_len -> nothing` is the same set of pairs.
+__global__ void __launch_bounds__(kBlock)
 k_bdpt_camera_shade(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B, const uint32_t* __restrict__ queue_in,
                     uint32_t* __restrict__ queue_out, float* __restrict__ film, unsigned long long* ctr, int parity)
 {
@@ -133,45 +142,39 @@ k_bdpt_camera_shade(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B,
         const size_t e = base + (threadIdx.x & 31);
         const bool valid = e < n;
         uint32_t slot = 0;
-        RayIn r; BdptPath st; Bsdf bsdf; V3 hit = v3(0, 0, 0), emit_c = v3(0, 0, 0);
-        bool emit = false, has_di = false; DiEntry di;
+        RayIn r; BdptPath st; Bsdf bsdf; V3 hit = v3(0, 0, 0), nrm = v3(0, 0, 0), emit_c = v3(0, 0, 0);
+        bool emit = false, has_di = false;
         int k = 0;
-        if (valid) {
-            slot = queue_in[e];
-            r = pool_load_ray(pool, slot);
-            bdpt_load(pool, B.dvc, slot, st);
-            k = bdpt_camera_pre(sc, P, r, st, pool.hit_prim[slot], pool.hit_t[slot], hit, bsdf, emit, emit_c, has_di, di);
-            if (emit) film_add(film, st.index, emit_c, P.film_scale);
-        }
-        const unsigned long long dpos = warp_append(&counters[WF_AUX_COUNT], valid && has_di);
-        if (valid && has_di) {
-            float4* d = B.di + 6 * dpos;
-            d[0] = make_float4(di.q[0], di.q[1], di.q[2], di.cA.x);
-            d[1] = make_float4(di.q[3], di.q[4], di.q[5], di.cA.y);
-            d[2] = make_float4(di.q[6], di.q[7], di.q[8], di.cA.z);
-            d[3] = make_float4(di.bo[0], di.bo[1], di.bo[2], di.cB.x);
-            d[4] = make_float4(di.bd[0], di.bd[1], di.bd[2], di.cB.y);
-            d[5] = make_float4(__int_as_float(di.has_B), __int_as_float(di.light_id), __uint_as_float(di.pixel), di.cB.z);
-        }
-        // connections to the stored vertices of this pixel's light path (warp-uniform trip count)
-        const int nv = (valid && k == 1) ? B.nverts[slot] : 0;
-        int nv_max = nv;
-        for (int o = 16; o > 0; o >>= 1) nv_max = max(nv_max, __shfl_xor_sync(0xffffffffu, nv_max, o));
-        bool stop = false;
-        for (int v = 0; v < nv_max; v++) {
-            bool has = false; Connection c;
-            if (v < nv && !stop) {
-                const float4* q = B.verts + ((size_t)v * B.n_paths + slot) * 4;
-                const float4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-                LightVertex lv;
-                lv.pos = v3(q0.x, q0.y, q0.z); lv.dVCM = q0.w; lv.throughput = v3(q1.x, q1.y, q1.z); lv.dVC = q1.w;
-                lv.wi = v3(q2.x, q2.y, q2.z); lv.matid = __float_as_int(q2.w); lv.n = v3(q3.x, q3.y, q3.z);
-                const int ls = __float_as_int(q3.w); lv.length = ls & 0xffff; lv.spec = ls >> 16;
-                if (lv.length + 1 + st.length > P.max_len) stop = true;                 // `break` :238-240
-                else if (lv.length + 1 + st.length >= P.min_len) has = bdpt_connect_vertices(sc, P, lv, bsdf, hit, st, c);
+        {
+            DiEntry di;
+            if (valid) {
+                slot = queue_in[e];
+                r = pool_load_ray(pool, slot);
+                bdpt_load(pool, B.dvc, slot, st);
+                k = bdpt_camera_pre(sc, P, r, st, pool.hit_prim[slot], pool.hit_t[slot], hit, nrm, bsdf, emit, emit_c, has_di, di);
+                if (emit) film_add(film, st.index, emit_c, P.film_scale);
             }
-            const unsigned long long cpos = warp_append(&counters[WF_SHADOW_COUNT], has);
-            if (has) conn_store(B.conn, cpos, c);
+            const unsigned long long dpos = warp_append(&counters[WF_AUX_COUNT], valid && has_di);
+            if (valid && has_di) {
+                float4* d = B.di + 6 * dpos;
+                d[0] = make_float4(di.q[0], di.q[1], di.q[2], di.cA.x);
+                d[1] = make_float4(di.q[3], di.q[4], di.q[5], di.cA.y);
+                d[2] = make_float4(di.q[6], di.q[7], di.q[8], di.cA.z);
+                d[3] = make_float4(di.bo[0], di.bo[1], di.bo[2], di.cB.x);
+                d[4] = make_float4(di.bd[0], di.bd[1], di.bd[2], di.cB.y);
+                d[5] = make_float4(__int_as_float(di.has_B), __int_as_float(di.light_id), __uint_as_float(di.pixel), di.cB.z);
+            }
+        }
+        // the record of this vertex for the connections to the stored vertices of this pixel's light path
+        const int nv = (valid && k == 1) ? B.nverts[slot] : 0;
+        const unsigned long long vpos = warp_append(&counters[WF_CV_COUNT], nv > 0);
+        if (nv > 0) {
+            const size_t np = B.n_paths;
+            B.cverts[0 * np + vpos] = make_float4(hit.x, hit.y, hit.z, st.dVCM);
+            B.cverts[1 * np + vpos] = make_float4(st.throughput.x, st.throughput.y, st.throughput.z, st.dVC);
+            B.cverts[2 * np + vpos] = make_float4(-r.dx, -r.dy, -r.dz, __int_as_float(bsdf.mat_id));
+            B.cverts[3 * np + vpos] = make_float4(nrm.x, nrm.y, nrm.z, __int_as_float(st.length | (st.spec << 16)));
+            B.cverts[4 * np + vpos] = make_float4(__uint_as_float(st.index), __uint_as_float(slot), __int_as_float(nv), 0.f);
         }
         bool alive = false;
         if (valid && k != 0) {
@@ -180,6 +183,64 @@ k_bdpt_camera_shade(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B,
         }
         const unsigned long long qpos = warp_append(&counters[WF_NEXT_COUNT], alive);
         if (alive) { bdpt_store(pool, B.dvc, slot, r, st); queue_out[qpos] = slot; }
+    }
+}
+
+// Work items are uniform (one bsdf pair each), so they are dealt to the blocks statically — no work-fetch atomic — and the
+// connection queue is appended to once per BLOCK pass (shared-memory scan of the four warp counts, one global atomic per 128
+// items instead of one per 32): with ~10 connections per camera vertex the per-warp atomics on two addresses were what the
+// kernel waited for.
+__global__ void __launch_bounds__(kBlock)
+k_bdpt_connect(DevSceneView sc, BdptParams P, BdptBuffers B, unsigned long long* ctr, int parity)
+{
+    unsigned long long* counters = wf_cur(ctr, parity);
+    const size_t n_cv = (size_t)counters[WF_CV_COUNT];
+    if (n_cv == 0) return;
+    const size_t n = n_cv * (size_t)B.maxv;          // work item i = (light vertex index i / n_cv, camera record i % n_cv)
+    const size_t np = B.n_paths;
+    __shared__ unsigned s_cnt[kBlock / 32];
+    __shared__ unsigned long long s_base;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (size_t i0 = (size_t)blockIdx.x * kBlock; i0 < n; i0 += (size_t)gridDim.x * kBlock) {      // block-uniform trip count
+        const size_t i = i0 + threadIdx.x;
+        bool has = false; Connection c;
+        if (i < n) {
+            const int v = (int)(i / n_cv);
+            const size_t rec = i - (size_t)v * n_cv;
+            const float4 c4 = B.cverts[4 * np + rec];
+            if (v < __float_as_int(c4.z)) {
+                const uint32_t slot = __float_as_uint(c4.y);
+                const float4* q = B.verts + ((size_t)v * np + slot) * 4;
+                const float4 q3 = q[3], c3 = B.cverts[3 * np + rec];
+                const int ls = __float_as_int(q3.w), cs = __float_as_int(c3.w);
+                const int lv_len = ls & 0xffff, cam_len = cs & 0xffff;
+                if (lv_len + 1 + cam_len <= P.max_len && lv_len + 1 + cam_len >= P.min_len) {
+                    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+                    const float4 c0 = B.cverts[0 * np + rec], c1 = B.cverts[1 * np + rec], c2 = B.cverts[2 * np + rec];
+                    LightVertex lv;
+                    lv.pos = v3(q0.x, q0.y, q0.z); lv.dVCM = q0.w; lv.throughput = v3(q1.x, q1.y, q1.z); lv.dVC = q1.w;
+                    lv.wi = v3(q2.x, q2.y, q2.z); lv.matid = __float_as_int(q2.w); lv.n = v3(q3.x, q3.y, q3.z);
+                    lv.length = lv_len; lv.spec = ls >> 16;
+                    BdptPath st;
+                    st.throughput = v3(c1.x, c1.y, c1.z); st.dVCM = c0.w; st.dVC = c1.w;
+                    st.length = cam_len; st.spec = cs >> 16; st.index = __float_as_uint(c4.x);
+                    Bsdf bsdf;
+                    bsdf_init(bsdf, v3(c2.x, c2.y, c2.z), v3(c3.x, c3.y, c3.z), __float_as_int(c2.w), sc);
+                    has = bdpt_connect_vertices(sc, P, lv, bsdf, v3(c0.x, c0.y, c0.z), st, c);
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) s_cnt[warp] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            for (int w = 0; w < kBlock / 32; w++) { const unsigned t = s_cnt[w]; s_cnt[w] = tot; tot += t; }
+            s_base = tot ? atomicAdd(&counters[WF_SHADOW_COUNT], (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        if (has) conn_store(B.conn, s_base + s_cnt[warp] + __popc(m & ((1u << lane) - 1u)), c);
+        __syncthreads();      // s_cnt / s_base are rewritten by the next pass
     }
 }
 
@@ -233,7 +294,7 @@ void bdpt_destroy(wrt_wavefront* wf)
     BdptBuffers* B = (BdptBuffers*)wf->bdpt;
     if (!B) return;
     cudaFree(B->dvc); cudaFree(B->verts); cudaFree(B->nverts);
-    cudaFree(B->conn.a); cudaFree(B->conn.b); cudaFree(B->conn.c); cudaFree(B->conn.pixel); cudaFree(B->di);
+    cudaFree(B->conn.a); cudaFree(B->conn.b); cudaFree(B->conn.c); cudaFree(B->conn.pixel); cudaFree(B->di); cudaFree(B->cverts);
     delete B;
     wf->bdpt = nullptr;
 }
@@ -249,6 +310,7 @@ static int bdpt_alloc(BdptBuffers* B, unsigned n_paths, int maxv)
     WRT_CUDA(cudaMalloc((void**)&B->conn.c, conn_cap * sizeof(float4)));
     WRT_CUDA(cudaMalloc((void**)&B->conn.pixel, conn_cap * sizeof(uint32_t)));
     WRT_CUDA(cudaMalloc((void**)&B->di, (size_t)n_paths * 6 * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->cverts, (size_t)n_paths * 5 * sizeof(float4)));
     return WRT_OK;
 }
 
@@ -352,6 +414,7 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
     const int g_ext_c = persistent_grid_for((const void*)k_pt_extend_count<false>, kBlock);
     const int g_ls = persistent_grid_for((const void*)k_bdpt_light_shade, kBlock);
     const int g_cs = persistent_grid_for((const void*)k_bdpt_camera_shade, kBlock);
+    const int g_cn = persistent_grid_for((const void*)k_bdpt_connect, kBlock);
     const int g_sh_p = persistent_grid_for((const void*)k_pt_shadow<true>, kBlock);
     const int g_sh_e = persistent_grid_for((const void*)k_pt_shadow<false>, kBlock);
     const int g_sh_c = persistent_grid_for((const void*)k_pt_shadow_count<false>, kBlock);
@@ -394,8 +457,10 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
                 if (ev) cudaEventRecord(ev[1], st);
                 if (phase == 0)
                     k_bdpt_light_shade<<<g_ls, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, Bv, wf->queue[cur], wf->queue[cur ^ 1], wf->counters, par);
-                else
+                else {
                     k_bdpt_camera_shade<<<g_cs, kBlock, 0, st>>>(sc->view, P, wf->pool, Bv, wf->queue[cur], wf->queue[cur ^ 1], d_film, wf->counters, par);
+                    k_bdpt_connect<<<g_cn, kBlock, 0, st>>>(sc->view, P, Bv, wf->counters, par);
+                }
                 if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[3], st); }
                 if (counting && count_pruned) k_pt_shadow_count<true><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par);
                 else if (counting) k_pt_shadow_count<false><<<g_sh_c, kBlock, 0, st>>>(sc->view, Bv.conn, d_film, P.film_scale, wf->counters, par);
@@ -407,7 +472,7 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
                 }
                 if (ev) { cudaEventRecord(ev[4], st); timed++; }
                 WRT_CUDA(cudaGetLastError());
-                sc->stats.kernel_launches += 3 + (phase == 1 ? 1 : 0);
+                sc->stats.kernel_launches += 3 + (phase == 1 ? 2 : 0);
                 cur ^= 1;
                 if ((it & 15) == 15 && it + 1 < phase_iters) {      // very long paths allowed (max_len > 15): look once every 16 iterations
                     WRT_CUDA(cudaMemcpyAsync(wf->h_counters, wf->counters + par * WF_BANK, WF_BANK * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

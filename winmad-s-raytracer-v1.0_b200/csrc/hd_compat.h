@@ -16,6 +16,8 @@
 #define WRT_HOSTSIM_VECTOR_TYPES
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = { x, y, z, w }; return r; }
+struct alignas(8) float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r = { x, y }; return r; }
 #endif
 #endif
 

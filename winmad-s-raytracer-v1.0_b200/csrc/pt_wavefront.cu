@@ -243,6 +243,35 @@ static int wavefront_alloc(wrt_wavefront* wf, int capacity)
     return WRT_OK;
 }
 
+// Experiment knob (off by default): WRT_L2_PERSIST_MB=<n> sets aside n MB of L2 for persisting lines and puts an access-policy
+// window over the kd nodes (WRT_L2_PERSIST_WHAT=recs: over the leaf records) on the traversal streams.  Best effort.
+static void apply_l2_window(wrt_scene* sc, cudaStream_t st)
+{
+    const char* e = getenv("WRT_L2_PERSIST_MB");
+    const long mb = e ? atol(e) : 0;
+    if (mb <= 0) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, sc->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, sc->device);
+    size_t want = (size_t)mb << 20;
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
+    if (want == 0 || max_window <= 0) return;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    const char* w = getenv("WRT_L2_PERSIST_WHAT");
+    const bool recs = w && w[0] == 'r';
+    size_t bytes = recs ? (size_t)sc->n_leaf_recs * 48 : (size_t)sc->view.n_nodes * 32 + 32;
+    if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    v.accessPolicyWindow.base_ptr = recs ? sc->d_leaf_recs : sc->d_nodes;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = bytes <= want ? 1.0f : (float)((double)want / (double)bytes);
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
+}
+
 int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** out)
 {
     wrt_wavefront** where = slot == 0 ? &sc->wf : &sc->wf_extra[slot - 1];
@@ -257,6 +286,8 @@ int wavefront_get_slot(wrt_scene* sc, int slot, int capacity, wrt_wavefront** ou
         return rc;
     }
     wf->capacity = capacity;
+    apply_l2_window(sc, wf->stream);
+    apply_l2_window(sc, wf->shadow_stream);
     *where = wf;
     *out = wf;
     return WRT_OK;

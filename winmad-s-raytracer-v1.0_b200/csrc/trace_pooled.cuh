@@ -51,6 +51,16 @@ constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 #define WRT_COOP_MIN_RECORDS 8
 #endif
 
+// Stack entries in the global scratch.  The reference pushes (far child, t, tmax) and, popping, restores all three
+// (KDtreeAccel.cpp:349-384).  tmax is redundant: it only ever changes in the push itself (tmax = t), so at any moment
+// T.tmax == the t of the entry below the top (or the root interval's tmax with an empty stack) — by induction over push / pop,
+// bit patterns copied, never recomputed.  WRT_STACK8 stores 8-byte entries (node, t) above a sentinel row that holds the root
+// tmax; a pop reads rows sp + 1 (node, tmin) and sp (tmax), two independent loads.  Half the L2 footprint and store traffic
+// of the 16-byte entries.
+#ifndef WRT_STACK8
+#define WRT_STACK8 1
+#endif
+
 struct PoolSmem {
     float4 a[kPoolRays];               // ox oy oz dx
     float4 b[kPoolRays];               // dy dz ray.tmin ray.tmax
@@ -158,6 +168,9 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                             sm.c[slot] = make_float4(T.ix, T.iy, T.iz, T.best);
                             sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(0), __int_as_float(T.degen ? (1 << 29) : 0));
                             sm.e[slot] = make_int4(-1, 0, 0, (int)item);
+#if WRT_STACK8
+                            reinterpret_cast<float2*>(gstack)[slot] = make_float2(0.f, T.tmax);     // sentinel row: root tmax
+#endif
                             started = true;
                         } else src.done(item, r, -1, WRT_INF);
                     }
@@ -261,7 +274,11 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                 bool need_pop = (spw >> 30) & 1;
                 T.res = sm.e[slot].x;                             // (rec, rec_end, item are only touched when the ray leaves this ring)
                 int leaf_first = 0, leaf_end = 0;
+#if WRT_STACK8
+                float2* stk = reinterpret_cast<float2*>(gstack) + slot;     // entry (sp, slot) at stk[(sp + 1) * kPoolRays]; row 0 = sentinel
+#else
                 float4* stk = gstack + slot;                      // entry (sp, slot) at stk[sp * kPoolRays]
+#endif
                 // (measured and dropped: unrolling this loop by 2 -1.4 %, fully -41 % (instruction cache); prefetch.global.L1
                 //  of the child pair right after the node header is known -19 % / -42 % for one / both children, of a
                 //  leaf's first records on leaf entry -4 %; a warp-uniform loop with a `live` flag instead of the breaks -4 %:
@@ -271,8 +288,14 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                         need_pop = false;
                         if (T.sp <= 0) { next = 2; break; }
                         --T.sp;
+#if WRT_STACK8
+                        const float2 q = stk[(unsigned)(T.sp + 1) * (unsigned)kPoolRays];
+                        const float2 below = stk[(unsigned)T.sp * (unsigned)kPoolRays];
+                        T.node = __float_as_int(q.x); T.tmin = q.y; T.tmax = below.y;
+#else
                         const float4 q = stk[(unsigned)T.sp * (unsigned)kPoolRays];
                         T.node = __float_as_int(q.x); T.tmin = q.y; T.tmax = q.z;
+#endif
                     }
                     if (r.tmax < T.tmin) { next = 2; break; }                              // KDtreeAccel.cpp:323
                     const float4* np = sc.nodes + 2 * (size_t)T.node;
@@ -301,7 +324,11 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                     const bool near_only = (t > T.tmax) || (t <= 0.f);
                     const bool far_only = !near_only && (t < T.tmin);
                     const bool both = !near_only && !far_only;
+#if WRT_STACK8
+                    if (both && T.sp < kPoolStack) { stk[(unsigned)(T.sp + 1) * (unsigned)kPoolRays] = make_float2(__int_as_float(far_n), t); ++T.sp; }
+#else
                     if (both && T.sp < kPoolStack) { stk[(unsigned)T.sp * (unsigned)kPoolRays] = make_float4(__int_as_float(far_n), t, T.tmax, 0.f); ++T.sp; }
+#endif
                     T.node = far_only ? far_n : near_n;
                     T.tmax = both ? t : T.tmax;
                 }

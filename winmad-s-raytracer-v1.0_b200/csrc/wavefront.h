@@ -21,6 +21,8 @@ enum {
     WF_GEN_COUNT = 6,   // PT: regenerated camera rays appended from the back of the next-bounce queue (BDPT: stays 0)
     WF_AUX2_COUNT = 7,  // BDPT: BSDF-sampled rays traced by the DI kernel
     WF_WORK4 = 8,       // BDPT DI kernel work fetch
+    WF_CV_COUNT = 9,    // BDPT: camera-vertex records written by the camera shade kernel for the connection kernel
+    WF_WORK5 = 10,      // BDPT connection kernel work fetch
     WF_BANK = 12,
     // ---- persistent part, after the two banks ----
     WF_PERSIST = 2 * WF_BANK,
