@@ -1,0 +1,24 @@
+#!/bin/bash
+# round 2, tenth GPU call: ray suspension with the priority run — parity of the PT tests, then tail-budget A/B
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_render.py tests/test_gpu_tape.py -m gpu -q -x -s -k "pt or PT or suspension" > gpurun_out/pytest_gpu_r2k.log 2>&1; echo "pytest rc=$?"; grep -a -E "passed|failed|handed over" gpurun_out/pytest_gpu_r2k.log | tail -4
+one() { # label workload spp steps env...
+  label=$1; w=$2; spp=$3; steps=$4; shift 4
+  extra=""; [ "$spp" != "0" ] && extra="--spp $spp"
+  env "$@" timeout 300 python bench.py --workload $w $extra --steps $steps --warmup 3 --no-cpu-baseline > gpurun_out/bench_${label}_${w}_$spp.json 2>gpurun_out/bench_${label}_${w}_$spp.err
+  python -c "
+import json
+try:
+    j=json.loads(open('gpurun_out/bench_${label}_${w}_$spp.json').read().strip().splitlines()[-1]); print('$label $w spp=$spp: %.1f Mrays/s %.3f ms/step launches %d' % (j['value'], j['ms_per_step'], j['gpu_launches']))
+except Exception as e: print('$label $w ERR', e)"
+}
+for b in 0 8 24 64 200; do
+  one pb$b c1 0 20 WRT_TAIL_BUDGET=$b
+  one pb$b c3 8 5 WRT_TAIL_BUDGET=$b
+  one pb$b c3 0 3 WRT_TAIL_BUDGET=$b
+done
+for b in 0 24; do
+  one pb$b torus 0 3 WRT_TAIL_BUDGET=$b
+  one pb$b c5_small 0 3 WRT_TAIL_BUDGET=$b
+done
+WRT_TAIL_BUDGET=24 python tools/c1_as_shipped.py > gpurun_out/c1_as_shipped_r2k.log 2>&1; cat gpurun_out/c1_as_shipped_r2k.log

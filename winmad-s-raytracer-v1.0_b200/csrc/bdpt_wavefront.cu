@@ -26,6 +26,7 @@ struct BdptBuffers {
     ShadowQueue conn; size_t conn_cap;
     float4* di; size_t di_cap;   // 6 float4 per entry
     float4* cverts;          // [5][n_paths] camera-vertex records of the current iteration (k_bdpt_connect)
+    uint32_t* pair_rec;      // [conn_cap] camera-vertex record of every (camera vertex, light vertex) pair, pairs of a record adjacent
 };
 
 __device__ __forceinline__ void bdpt_store(const PathPool& pool, float* dvc, uint32_t slot, const RayIn& r, const BdptPath& st)
@@ -168,13 +169,24 @@ k_bdpt_camera_shade(DevSceneView sc, BdptParams P, PathPool pool, BdptBuffers B,
         // the record of this vertex for the connections to the stored vertices of this pixel's light path
         const int nv = (valid && k == 1) ? B.nverts[slot] : 0;
         const unsigned long long vpos = warp_append(&counters[WF_CV_COUNT], nv > 0);
+        // ... and its nv pairs in the pair list (warp scan of nv, one atomic per warp): the connection kernel then has one VALID
+        // pair per lane (a [light vertex][record] grid left 12 of 32 lanes busy: most light paths are shorter than the longest)
+        unsigned incl = (unsigned)nv;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned long long pbase = 0;
+        if (total) {
+            if ((threadIdx.x & 31) == 31) pbase = atomicAdd(&counters[WF_PAIR_COUNT], (unsigned long long)total);
+            pbase = __shfl_sync(0xffffffffu, pbase, 31) + (incl - (unsigned)nv);
+        }
         if (nv > 0) {
+            for (int q = 0; q < nv; q++) B.pair_rec[pbase + q] = (uint32_t)vpos;
             const size_t np = B.n_paths;
             B.cverts[0 * np + vpos] = make_float4(hit.x, hit.y, hit.z, st.dVCM);
             B.cverts[1 * np + vpos] = make_float4(st.throughput.x, st.throughput.y, st.throughput.z, st.dVC);
             B.cverts[2 * np + vpos] = make_float4(-r.dx, -r.dy, -r.dz, __int_as_float(bsdf.mat_id));
             B.cverts[3 * np + vpos] = make_float4(nrm.x, nrm.y, nrm.z, __int_as_float(st.length | (st.spec << 16)));
-            B.cverts[4 * np + vpos] = make_float4(__uint_as_float(st.index), __uint_as_float(slot), __int_as_float(nv), 0.f);
+            B.cverts[4 * np + vpos] = make_float4(__uint_as_float(st.index), __uint_as_float(slot), __int_as_float(nv), __uint_as_float((uint32_t)pbase));
         }
         bool alive = false;
         if (valid && k != 0) {
@@ -194,9 +206,8 @@ __global__ void __launch_bounds__(kBlock)
 k_bdpt_connect(DevSceneView sc, BdptParams P, BdptBuffers B, unsigned long long* ctr, int parity)
 {
     unsigned long long* counters = wf_cur(ctr, parity);
-    const size_t n_cv = (size_t)counters[WF_CV_COUNT];
-    if (n_cv == 0) return;
-    const size_t n = n_cv * (size_t)B.maxv;          // work item i = (light vertex index i / n_cv, camera record i % n_cv)
+    const size_t n = (size_t)counters[WF_PAIR_COUNT];      // work item i = pair i of the list k_bdpt_camera_shade wrote
+    if (n == 0) return;
     const size_t np = B.n_paths;
     __shared__ unsigned s_cnt[kBlock / 32];
     __shared__ unsigned long long s_base;
@@ -205,10 +216,10 @@ k_bdpt_connect(DevSceneView sc, BdptParams P, BdptBuffers B, unsigned long long*
         const size_t i = i0 + threadIdx.x;
         bool has = false; Connection c;
         if (i < n) {
-            const int v = (int)(i / n_cv);
-            const size_t rec = i - (size_t)v * n_cv;
+            const size_t rec = B.pair_rec[i];
             const float4 c4 = B.cverts[4 * np + rec];
-            if (v < __float_as_int(c4.z)) {
+            const int v = (int)((uint32_t)i - __float_as_uint(c4.w));          // the record's pairs are adjacent: its light vertices 0 .. nv-1
+            {
                 const uint32_t slot = __float_as_uint(c4.y);
                 const float4* q = B.verts + ((size_t)v * np + slot) * 4;
                 const float4 q3 = q[3], c3 = B.cverts[3 * np + rec];
@@ -294,7 +305,7 @@ void bdpt_destroy(wrt_wavefront* wf)
     BdptBuffers* B = (BdptBuffers*)wf->bdpt;
     if (!B) return;
     cudaFree(B->dvc); cudaFree(B->verts); cudaFree(B->nverts);
-    cudaFree(B->conn.a); cudaFree(B->conn.b); cudaFree(B->conn.c); cudaFree(B->conn.pixel); cudaFree(B->di); cudaFree(B->cverts);
+    cudaFree(B->conn.a); cudaFree(B->conn.b); cudaFree(B->conn.c); cudaFree(B->conn.pixel); cudaFree(B->di); cudaFree(B->cverts); cudaFree(B->pair_rec);
     delete B;
     wf->bdpt = nullptr;
 }
@@ -311,6 +322,7 @@ static int bdpt_alloc(BdptBuffers* B, unsigned n_paths, int maxv)
     WRT_CUDA(cudaMalloc((void**)&B->conn.pixel, conn_cap * sizeof(uint32_t)));
     WRT_CUDA(cudaMalloc((void**)&B->di, (size_t)n_paths * 6 * sizeof(float4)));
     WRT_CUDA(cudaMalloc((void**)&B->cverts, (size_t)n_paths * 5 * sizeof(float4)));
+    WRT_CUDA(cudaMalloc((void**)&B->pair_rec, conn_cap * sizeof(uint32_t)));
     return WRT_OK;
 }
 
@@ -452,8 +464,8 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
                 if (ev) cudaEventRecord(ev[0], st);
                 if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, 0);
                 else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, 0);
-                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0);
-                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0);
+                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0, ExtendSuspend());
+                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0, ExtendSuspend());
                 if (ev) cudaEventRecord(ev[1], st);
                 if (phase == 0)
                     k_bdpt_light_shade<<<g_ls, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, Bv, wf->queue[cur], wf->queue[cur ^ 1], wf->counters, par);

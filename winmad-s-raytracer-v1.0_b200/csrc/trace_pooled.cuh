@@ -72,6 +72,23 @@ struct PoolSmem {
 
 constexpr size_t kPoolStackBytesPerWarp = (size_t)kPoolStack * kPoolRays * sizeof(float4);
 
+// Rays carried over to the NEXT launch of the same queue (work sources with Src::kCanSuspend, i.e. the path tracer's extend
+// kernel).  A launch ends when its longest ray ends, and on the scenes here a handful of rays are 30-50x longer than the mean
+// (grazing rays that pierce hundreds of leaves): ~3.5 ms of tail per launch on the 1 M-triangle scene, ~0.9 ms of a 0.9 ms
+// launch on torus.scene as shipped.  Once a warp is in its tail loop (work counter exhausted, <= WRT_COOP_RAYS rays left) it
+// serves them for at most Src::tail_budget() more rounds, then writes the complete traversal state of what is left — the 80
+// bytes of PoolSmem and rows 0..sp of the ray's stack — to a record and returns.  The work source marks the work item
+// (`suspended`), the wavefront re-queues it untouched, and the next launch's refill restores the record into a slot
+// (`resume_id`) and goes on exactly where the ray stopped: same state, same steps, same result — the traversal is only cut
+// into two launches, the long ray now runs beside the next launch's bulk instead of holding this launch open.
+struct SuspendBuf {
+    float4* state;             // [5][cap]: a b c d e of PoolSmem
+    float2* stack;             // [kPoolStack + 1][cap]: rows 0..sp of the 8-byte stack (row 0 = sentinel)
+    unsigned cap;
+};
+constexpr size_t suspend_state_bytes(unsigned cap) { return (size_t)5 * cap * sizeof(float4); }
+constexpr size_t suspend_stack_bytes(unsigned cap) { return (size_t)(kPoolStack + 1) * cap * sizeof(float2); }
+
 // One cooperative pass over the rest of a ray's leaf (see WRT_COOP_RAYS); only the tail loop (pooled_tail, out of line) calls it.
 // Returns true when the query was decided and consumed (boolean queries); otherwise the ray goes back to the node ring.
 template <class Src>
@@ -141,6 +158,8 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
     const unsigned RM = kPoolRays - 1;
     unsigned hn = R.hn, tn = R.tn, hp = R.hp, tp = R.tp, hf = R.hf, tf = R.tf;
     bool exhausted = TAIL;
+    unsigned rounds = 0u, budget = 0u;
+    if constexpr (TAIL && Src::kCanSuspend) budget = src.tail_budget();
 
     for (;;) {
         // ---- refill free slots from the global work counter ------------------------------------
@@ -156,11 +175,31 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                 unsigned slot = 0;
                 if (have) slot = sm.ring[2][(hf + k) & RM];
                 __syncwarp();
-                bool started = false;
+                bool started = false, to_prim = false;
                 const size_t item = (size_t)base + k;
                 if (have && item < n) {
+                    bool resumed = false;
+#if WRT_STACK8
+                    if constexpr (Src::kCanSuspend) {
+                        const int rid = src.resume_id(item);
+                        if (rid >= 0) {      // a ray suspended by the previous launch: restore its record into this slot
+                            const SuspendBuf sb = src.susp_in();
+                            const size_t c = sb.cap;
+                            sm.a[slot] = sb.state[0 * c + rid]; sm.b[slot] = sb.state[1 * c + rid]; sm.c[slot] = sb.state[2 * c + rid];
+                            const float4 d = sb.state[3 * c + rid];
+                            sm.d[slot] = d;
+                            float4 e4 = sb.state[4 * c + rid];
+                            const int rec = __float_as_int(e4.y), rec_end = __float_as_int(e4.z);
+                            sm.e[slot] = make_int4(__float_as_int(e4.x), rec, rec_end, (int)item);
+                            const int sp = __float_as_int(d.w) & 0xffff;
+                            float2* col = reinterpret_cast<float2*>(gstack) + slot;
+                            for (int q = 0; q <= sp; q++) col[(unsigned)q * (unsigned)kPoolRays] = sb.stack[(size_t)q * c + rid];
+                            started = true; resumed = true; to_prim = rec < rec_end;
+                        }
+                    }
+#endif
                     RayIn r;
-                    if (src.load(item, r)) {
+                    if (!resumed && src.load(item, r)) {
                         Trav T;
                         if (trav_begin(sc, r, T)) {
                             sm.a[slot] = make_float4(r.ox, r.oy, r.oz, r.dx);
@@ -175,9 +214,14 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                         } else src.done(item, r, -1, WRT_INF);
                     }
                 }
-                const unsigned bs = __ballot_sync(FULL, started);
-                if (started) sm.ring[0][(tn + __popc(bs & lt)) & RM] = (unsigned char)slot;
+                const unsigned bs = __ballot_sync(FULL, started && !to_prim);
+                if (started && !to_prim) sm.ring[0][(tn + __popc(bs & lt)) & RM] = (unsigned char)slot;
                 tn += __popc(bs);
+                if constexpr (Src::kCanSuspend) {
+                    const unsigned bp = __ballot_sync(FULL, started && to_prim);
+                    if (started && to_prim) sm.ring[1][(tp + __popc(bp & lt)) & RM] = (unsigned char)slot;
+                    tp += __popc(bp);
+                }
                 const unsigned bf = __ballot_sync(FULL, have && !started);
                 if (have && !started) sm.ring[2][(tf + __popc(bf & lt)) & RM] = (unsigned char)slot;
                 tf += __popc(bf);
@@ -191,6 +235,36 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
             continue;
         }
         if (!TAIL && WRT_COOP_RAYS > 0 && exhausted && cn + cp <= (unsigned)WRT_COOP_RAYS) break;     // the tail loop takes over
+#if WRT_STACK8
+        if constexpr (TAIL && Src::kCanSuspend) {
+            if (budget != 0u && ++rounds > budget) {
+                // ---- out of budget: what is left goes to the next launch (SuspendBuf above) -----------------------------
+                const unsigned cnt = cn + cp;                    // <= WRT_COOP_RAYS <= 32
+                const SuspendBuf sb = src.susp_out();
+                unsigned long long first = 0;
+                if (lane == 0) first = atomicAdd(src.susp_counter(), (unsigned long long)cnt);
+                first = __shfl_sync(FULL, first, 0);
+                if (first + cnt <= (unsigned long long)sb.cap) {
+                    if (lane < cnt) {
+                        const unsigned slot = lane < cn ? sm.ring[0][(hn + lane) & RM] : sm.ring[1][(hp + (lane - cn)) & RM];
+                        const size_t c = sb.cap, id = (size_t)first + lane;
+                        const float4 d = sm.d[slot];
+                        const int4 e = sm.e[slot];
+                        sb.state[0 * c + id] = sm.a[slot]; sb.state[1 * c + id] = sm.b[slot]; sb.state[2 * c + id] = sm.c[slot];
+                        sb.state[3 * c + id] = d;
+                        sb.state[4 * c + id] = make_float4(__int_as_float(e.x), __int_as_float(e.y), __int_as_float(e.z), 0.f);
+                        const int sp = __float_as_int(d.w) & 0xffff;
+                        const float2* col = reinterpret_cast<const float2*>(gstack) + slot;
+                        for (int q = 0; q <= sp; q++) sb.stack[(size_t)q * c + id] = col[(unsigned)q * (unsigned)kPoolRays];
+                        src.suspended((size_t)(unsigned)e.w, (unsigned)id);
+                    }
+                    hn = tn; hp = tp;
+                    break;
+                }
+                budget = 0u;       // the record buffer is full: finish these rays here
+            }
+        }
+#endif
         // (a ray with a short rest of a leaf is served as well by the ordinary primitive round, which takes all waiting rays at once)
         if (TAIL && cp > 0 && (cp == 1u || sm.e[sm.ring[1][hp & RM]].z - sm.e[sm.ring[1][hp & RM]].y >= WRT_COOP_MIN_RECORDS)) {
             // ---- cooperative leaf pass (tail of the launch): the whole warp works on the FIRST ray of the prim ring --------
