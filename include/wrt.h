@@ -117,7 +117,6 @@ typedef struct {
     /* multi-GPU renders (wrt_init with more than one device): */
     double reduce_ms;          /* device time of the film exchange (peer films summed onto device 0) of the last render */
     uint64_t devices_used;     /* devices the last render ran on */
-    uint64_t suspended_rays;   /* closest-hit rays an extend launch of the last PT render handed over to its next launch (each is counted once in closest_rays) */
 } wrt_stats;
 
 typedef struct wrt_scene wrt_scene;           /* device-resident scene */

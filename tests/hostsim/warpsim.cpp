@@ -87,7 +87,6 @@ namespace wrt { void set_error(const std::string&) {} }
 struct WsClosestSrc {
     const wrt_ray* rays; int32_t* prim; float* t_out;
     static constexpr bool kCanDecide = false;
-    static constexpr bool kCanSuspend = false;
     void target(size_t, float&, float&, float&) const {}
     bool decided(const RayIn&, float) const { return false; }
     bool load(size_t i, RayIn& r) const
@@ -103,7 +102,6 @@ struct WsOccludedSrc {
     const float* q9; uint8_t* occluded;
     float tx, ty, tz;      // scheduler 2 keeps the target of the lane's ray here
     static constexpr bool kCanDecide = true;
-    static constexpr bool kCanSuspend = false;
     void target(size_t i, float& x, float& y, float& z) const { x = q9[9 * i + 6]; y = q9[9 * i + 7]; z = q9[9 * i + 8]; }
     bool load(size_t i, RayIn& r)
     {
@@ -123,31 +121,6 @@ struct WsOccludedSrc {
         }
         occluded[i] = vis ? 0 : 1;
     }
-};
-
-// Work source with ray suspension (the path tracer's ExtendSrc, host flavour): work item -> (ray, record to resume or -1).
-struct WsSuspendSrc {
-    const wrt_ray* rays; int32_t* prim; float* t_out;
-    const int* item_ray; const int* item_resume;
-    int* out_ray;                 // record id -> ray index, for the next launch
-    SuspendBuf in, out; unsigned long long* counter; unsigned budget;
-    static constexpr bool kCanDecide = false;
-    static constexpr bool kCanSuspend = true;
-    unsigned tail_budget() const { return budget; }
-    const SuspendBuf& susp_in() const { return in; }
-    const SuspendBuf& susp_out() const { return out; }
-    unsigned long long* susp_counter() const { return counter; }
-    int resume_id(size_t i) const { return item_resume[i]; }
-    void suspended(size_t i, unsigned id) const { out_ray[id] = item_ray[i]; }
-    void target(size_t, float&, float&, float&) const {}
-    bool decided(const RayIn&, float) const { return false; }
-    bool load(size_t i, RayIn& r) const
-    {
-        const wrt_ray& q = rays[item_ray[i]];
-        r.ox = q.ox; r.oy = q.oy; r.oz = q.oz; r.dx = q.dx; r.dy = q.dy; r.dz = q.dz; r.tmin = q.tmin; r.tmax = q.tmax;
-        return true;
-    }
-    void done(size_t i, const RayIn&, int id, float t) const { prim[item_ray[i]] = id; t_out[item_ray[i]] = t; }
 };
 
 struct WsScene { SceneLayout L; };
@@ -193,35 +166,6 @@ void ws_trace_closest(void* hv, const wrt_ray* rays, size_t n, int pruned, int s
     const DevSceneView& sc = ((WsScene*)hv)->L.view;
     WsClosestSrc src = { rays, prim, t };
     if (pruned) ws_run<true>(sc, src, n, sched); else ws_run<false>(sc, src, n, sched);
-}
-
-// Closest hits through a chain of launches: every launch takes `chunk` fresh rays plus the rays the previous launch suspended
-// (tail budget `budget` rounds).  Returns the number of launches; *n_suspended counts the hand-overs.
-int ws_trace_closest_suspend(void* hv, const wrt_ray* rays, size_t n, int pruned, unsigned budget, size_t chunk, int32_t* prim, float* t,
-                             unsigned long long* n_suspended)
-{
-    const DevSceneView& sc = ((WsScene*)hv)->L.view;
-    const unsigned cap = 64;
-    std::vector<float4> st[2] = { std::vector<float4>(5 * cap), std::vector<float4>(5 * cap) };
-    std::vector<float2> sk[2] = { std::vector<float2>((size_t)(kPoolStack + 1) * cap), std::vector<float2>((size_t)(kPoolStack + 1) * cap) };
-    std::vector<int> carried[2] = { std::vector<int>(cap), std::vector<int>(cap) };
-    size_t next = 0, n_carried = 0;
-    int launches = 0, cur = 0;
-    *n_suspended = 0;
-    while (next < n || n_carried > 0) {
-        std::vector<int> item_ray, item_resume;
-        for (size_t i = 0; i < n_carried; i++) { item_ray.push_back(carried[cur ^ 1][i]); item_resume.push_back((int)i); }
-        for (size_t i = 0; i < chunk && next < n; i++, next++) { item_ray.push_back((int)next); item_resume.push_back(-1); }
-        unsigned long long counter = 0;
-        WsSuspendSrc src = { rays, prim, t, item_ray.data(), item_resume.data(), carried[cur].data(),
-                             { st[cur ^ 1].data(), sk[cur ^ 1].data(), cap }, { st[cur].data(), sk[cur].data(), cap }, &counter, budget };
-        if (pruned) ws_run<true>(sc, src, item_ray.size(), 3); else ws_run<false>(sc, src, item_ray.size(), 3);
-        n_carried = (size_t)std::min<unsigned long long>(counter, cap);
-        *n_suspended += n_carried;
-        cur ^= 1;
-        if (++launches > 100000) return -1;
-    }
-    return launches;
 }
 
 void ws_trace_occluded(void* hv, const float* q9, size_t n, int pruned, int sched, uint8_t* occ)

@@ -37,18 +37,6 @@ class WarpSim:
                                prim.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
         return prim, t
 
-    def trace_closest_suspend(self, rays8, pruned=True, budget=1, chunk=48):
-        """Pooled scheduler with ray suspension: a chain of launches of `chunk` fresh rays each + the rays the previous launch
-        suspended after `budget` tail rounds.  Returns (prim, t, launches, hand-overs)."""
-        r = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)
-        prim = np.full(len(r), -7, np.int32); t = np.zeros(len(r), np.float32)
-        ns = C.c_ulonglong(0)
-        f = lib().ws_trace_closest_suspend
-        f.restype = C.c_int
-        launches = f(self.h, r.ctypes.data_as(C.c_void_p), C.c_size_t(len(r)), int(bool(pruned)), C.c_uint(budget), C.c_size_t(chunk),
-                     prim.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), C.byref(ns))
-        return prim, t, launches, ns.value
-
     def trace_occluded(self, q9, pruned=True, sched=3):
         q = np.ascontiguousarray(q9, np.float32).reshape(-1, 9)
         occ = np.full(len(q), 7, np.uint8)

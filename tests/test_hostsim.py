@@ -221,27 +221,6 @@ def test_warpsim_schedulers_match_port(wrt, monkeypatch, sched):
     assert np.array_equal(got[0], z["P_prim"][sel]) and np.array_equal(util.bits(got[1]), util.bits(z["P_t"][sel]))
 
 
-def test_warpsim_ray_suspension_is_invisible(wrt, monkeypatch):
-    """Ray suspension of the pooled scheduler (trace_pooled.cuh, SuspendBuf) on the CPU: launches of 48 fresh rays, a tail budget of
-    1 / 3 rounds, so that most launches hand rays over — from the node ring and from inside leaves, with non-empty stacks — and
-    the next launch resumes them.  Every ray's answer must still be the oracle's, bit for bit (PRUNED and EXACT)."""
-    from warpsim_py import WarpSim
-    monkeypatch.setenv("WRT_LEAF_SKIP_MIN", "3"); monkeypatch.setenv("WRT_LEAF_SKIP_CHUNK", "2")
-    sc, z = scenes.load_fixture("mixed_torus")
-    hs = util.host_scene(wrt, sc)
-    ws = WarpSim(hs.desc(), hs)
-    port = engines.PortEngine(wrt, sc)
-    rays = wrt.make_rays(engines.adversarial_rays(sc, 1500, seed=9))
-    want = port.intersect(rays)
-    for pruned, budget in ((True, 1), (True, 3), (False, 1)):
-        prim, t, launches, handed = ws.trace_closest_suspend(rays, pruned, budget, 48)
-        assert launches > 0 and handed > 20, (launches, handed)          # the path under test was taken
-        assert np.array_equal(prim, want[0]) and np.array_equal(util.bits(t), util.bits(want[1])), (pruned, budget)
-    # budget 0 = never suspend: one launch per chunk
-    prim, t, launches, handed = ws.trace_closest_suspend(rays[:200], True, 0, 48)
-    assert handed == 0 and launches == 5 and np.array_equal(prim, want[0][:200])
-
-
 def test_warpsim_nan_interval_and_tiny_batches(wrt):
     """Pooled scheduler on the CPU: the NaN-interval regression rays (tests above) and batches smaller than a warp / than the
     refill threshold (1, 5, 33 rays) — exhaustion and partially filled rings."""

@@ -83,7 +83,7 @@ class Stats(C.Structure):
                 ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64), ("last_render_ms", C.c_double),
                 ("last_trace_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
                 ("shadow_ms", C.c_double), ("extend_launches", C.c_uint64), ("extend_rays", C.c_uint64),
-                ("reduce_ms", C.c_double), ("devices_used", C.c_uint64), ("suspended_rays", C.c_uint64)]
+                ("reduce_ms", C.c_double), ("devices_used", C.c_uint64)]
 
 
 EXPORTS = [

@@ -464,8 +464,8 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
                 if (ev) cudaEventRecord(ev[0], st);
                 if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, 0);
                 else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, 0);
-                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0, ExtendSuspend());
-                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0, ExtendSuspend());
+                else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0);
+                else k_pt_extend<false><<<g_ext_e, kBlock, 0, st>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, 0);
                 if (ev) cudaEventRecord(ev[1], st);
                 if (phase == 0)
                     k_bdpt_light_shade<<<g_ls, kBlock, 0, st>>>(sc->view, P, dc, wf->pool, Bv, wf->queue[cur], wf->queue[cur ^ 1], wf->counters, par);

@@ -108,7 +108,7 @@ int multi_render(wrt_scene* sc, size_t floats, int n_units, const std::function<
         a.closest_rays += b.closest_rays; a.shadow_rays += b.shadow_rays; a.samples += b.samples; a.kernel_launches += b.kernel_launches;
         a.inner_visits += b.inner_visits; a.leaf_visits += b.leaf_visits; a.tri_tests += b.tri_tests; a.sphere_tests += b.sphere_tests;
         a.extend_ms += b.extend_ms; a.shade_ms += b.shade_ms; a.shadow_ms += b.shadow_ms;
-        a.extend_launches += b.extend_launches; a.extend_rays += b.extend_rays; a.suspended_rays += b.suspended_rays;
+        a.extend_launches += b.extend_launches; a.extend_rays += b.extend_rays;
         memset(&b, 0, sizeof b);
     }
     sc->stats.last_render_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

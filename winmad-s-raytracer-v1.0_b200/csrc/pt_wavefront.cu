@@ -56,11 +56,11 @@ k_pt_init(PtParams P, DevCamera cam, PathPool pool, uint32_t* queue, unsigned n0
 __global__ void __launch_bounds__(kBlock)
 k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint32_t* __restrict__ queue_in,
            uint32_t* __restrict__ queue_out, ShadowQueue sq, float* __restrict__ film, unsigned long long* ctr, int parity,
-           unsigned long long* next_sample, size_t cap, const uint32_t* __restrict__ resq_in, uint32_t* __restrict__ resq_out)
+           unsigned long long* next_sample, size_t cap)
 {
     const unsigned long long* prev = wf_prev(ctr, parity);
     unsigned long long* counters = wf_cur(ctr, parity);
-    const size_t n = wf_queue_n(prev), n_gen_in = (size_t)prev[WF_GEN_COUNT], n_res_in = (size_t)prev[WF_RES_COUNT];
+    const size_t n = wf_queue_n(prev), n_gen_in = (size_t)prev[WF_GEN_COUNT];
     size_t base;
     while (next_chunk(&counters[WF_WORK2], n, base)) {
         const size_t e = base + (threadIdx.x & 31);
@@ -68,25 +68,12 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
         uint32_t slot = 0;
         RayIn r; PathData pd; ShadeOut out;
         out.alive = false; out.emit = false; out.shadow = false;
-        bool susp = false;       // the extend kernel handed this ray over to its next launch (ExtendSrc::suspended): nothing to shade yet
         if (valid) {
-            slot = e < n_res_in ? resq_in[e] : queue_slot(queue_in, e - n_res_in, n_gen_in, cap);
-            const int hp = pool.hit_prim[slot];
-            susp = hp <= -2;
-            if (!susp) {
-                r = pool_load_ray(pool, slot);
-                pool_load_data(pool, slot, pd);
-                pt_shade(sc, P, r, pd, hp, pool.hit_t[slot], out);
-                if (out.emit) film_add(film, pd.pixel, out.emit_c, P.film_scale);
-            }
-        }
-        {   // ... its slot goes to the priority run of the next queue; the path state is not touched
-            const unsigned ms = __ballot_sync(0xffffffffu, susp);
-            if (ms) {
-                if ((threadIdx.x & 31) == 0) atomicAdd(&ctr[WF_TOTAL_SUSP], (unsigned long long)__popc(ms));
-                const unsigned long long rpos = warp_append(&counters[WF_RES_COUNT], susp);
-                if (susp) resq_out[rpos] = slot;
-            }
+            slot = queue_slot(queue_in, e, n_gen_in, cap);
+            r = pool_load_ray(pool, slot);
+            pool_load_data(pool, slot, pd);
+            pt_shade(sc, P, r, pd, pool.hit_prim[slot], pool.hit_t[slot], out);
+            if (out.emit) film_add(film, pd.pixel, out.emit_c, P.film_scale);
         }
         // NEE connection -> shadow queue
         const unsigned long long spos = warp_append(&counters[WF_SHADOW_COUNT], valid && out.shadow);
@@ -98,7 +85,7 @@ k_pt_shade(DevSceneView sc, PtParams P, DevCamera cam, PathPool pool, const uint
         }
         // path regeneration: a finished path's slot takes the next camera sample
         const bool alive = valid && out.alive;
-        const bool dead = valid && !out.alive && !susp;
+        const bool dead = valid && !out.alive;
         const unsigned long long snew = warp_append(next_sample, dead);
         const bool regen = dead && snew < P.total_samples;
         if (regen) pt_generate(P, cam, snew, r, pd);
@@ -253,12 +240,6 @@ static int wavefront_alloc(wrt_wavefront* wf, int capacity)
     WRT_CUDA(cudaEventCreateWithFlags(&wf->join_ev, cudaEventDisableTiming));
     WRT_CUDA(cudaEventCreateWithFlags(&wf->poll_ev[0], cudaEventDisableTiming));
     WRT_CUDA(cudaEventCreateWithFlags(&wf->poll_ev[1], cudaEventDisableTiming));
-    wf->susp_cap = (unsigned)std::min<size_t>(P / 16 + 4096, (size_t)1 << 18);      // a launch suspends at most WRT_COOP_RAYS rays per resident warp
-    for (int i = 0; i < 2; i++) {
-        WRT_CUDA(cudaMalloc(&wf->susp_state[i], suspend_state_bytes(wf->susp_cap)));
-        WRT_CUDA(cudaMalloc(&wf->susp_stack[i], suspend_stack_bytes(wf->susp_cap)));
-        WRT_CUDA(cudaMalloc((void**)&wf->resq[i], (size_t)wf->susp_cap * sizeof(uint32_t)));
-    }
     return WRT_OK;
 }
 
@@ -360,7 +341,6 @@ static void wavefront_free(wrt_wavefront* wf)
     bdpt_destroy(wf);
     cudaFree(wf->pool.ray); cudaFree(wf->pool.weight_pdf); cudaFree(wf->pool.meta);
     cudaFree(wf->pool.hit_prim); cudaFree(wf->pool.hit_t);
-    for (int i = 0; i < 2; i++) { cudaFree(wf->susp_state[i]); cudaFree(wf->susp_stack[i]); cudaFree(wf->resq[i]); }
     cudaFree(wf->queue[0]); cudaFree(wf->queue[1]);
     cudaFree(wf->shadow.a); cudaFree(wf->shadow.b); cudaFree(wf->shadow.c); cudaFree(wf->shadow.pixel);
     cudaFree(wf->shadow2.a); cudaFree(wf->shadow2.b); cudaFree(wf->shadow2.c); cudaFree(wf->shadow2.pixel); cudaFree(wf->trav_scratch2);
@@ -558,12 +538,7 @@ int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* 
     const bool regenerates = P.total_samples > first;       // some slot will take a second camera sample
     // Without regeneration a path slot lives for at most max_depth + 1 vertices (+ the emitter hit that ends it): the number
     // of iterations is known up front and nothing has to be read back at all.
-    // Ray suspension (trace_pooled.cuh): tail rounds a warp spends on its last rays before it hands them to the next launch.
-    unsigned tail_budget = 48u;
-    if (const char* e = getenv("WRT_TAIL_BUDGET")) tail_budget = (unsigned)std::max(0, atoi(e));
-    if (whitted || counting || !pruned || WRT_STACK8 == 0 || WRT_TRACE_SCHED != 3) tail_budget = 0u;      // (EXACT mode stays the plain A/B reference)
-    // (a suspended ray adds iterations to its path, so the count is only known up front without suspension)
-    const int fixed_iters = (regenerates || tail_budget) ? 0 : (whitted ? 0 : P.max_depth + 2);
+    const int fixed_iters = regenerates ? 0 : (whitted ? 0 : P.max_depth + 2);
 
     // one iteration of sub-pool s: extend -> shade -> shadow on the sub-pool's stream, all lengths read on the device
     auto enqueue_iteration = [&](SubState& s) -> int {
@@ -582,19 +557,13 @@ int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* 
         if (ev) cudaEventRecord(ev[0], q);
         if (counting && count_pruned) k_pt_extend_count<true><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, cap);
         else if (counting) k_pt_extend_count<false><<<g_ext_c, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, cap);
-        else if (pruned) {
-            ExtendSuspend sus;
-            sus.in = { (float4*)wf->susp_state[par ^ 1], (float2*)wf->susp_stack[par ^ 1], wf->susp_cap };
-            sus.out = { (float4*)wf->susp_state[par], (float2*)wf->susp_stack[par], wf->susp_cap };
-            sus.counter = nullptr; sus.budget = tail_budget; sus.resq = wf->resq[cur];
-            k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, cap, sus);
-        }
-        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, cap, ExtendSuspend());
+        else if (pruned) k_pt_extend<true><<<g_ext_p, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, cap);
+        else k_pt_extend<false><<<g_ext_e, kBlock, 0, q>>>(sc->view, wf->pool, wf->queue[cur], wf->counters, par, (float4*)wf->trav_scratch, cap);
         if (ev) cudaEventRecord(ev[1], q);
         if (whitted) k_wh_shade<<<g_wshade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], wf->queue[cur ^ 1], sq,
                                                             d_film, wf->counters, par, next_sample, cap, wh_pend[s.index], wh_levels);
         else k_pt_shade<<<g_shade, kBlock, 0, q>>>(sc->view, P, dc, wf->pool, wf->queue[cur], wf->queue[cur ^ 1], sq,
-                                                   d_film, wf->counters, par, next_sample, cap, wf->resq[cur], wf->resq[cur ^ 1]);
+                                                   d_film, wf->counters, par, next_sample, cap);
         if (ev) cudaEventRecord(ev[2], q);
         WRT_CUDA(cudaEventRecord(wf->shaded_ev[par], q));
         // the shadow kernel: its own stream, overlapping the next iteration's extend + shade
@@ -659,15 +628,13 @@ int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* 
         WRT_CUDA(cudaStreamWaitEvent(st, sub[j].wf->join_ev, 0));
     }
     // ray counts of the render: accumulated on the device, read once
-    sc->stats.extend_launches = 0; sc->stats.extend_rays = 0; sc->stats.suspended_rays = 0;
+    sc->stats.extend_launches = 0; sc->stats.extend_rays = 0;
     for (int j = 0; j < plan.k; j++) {
-        unsigned long long h[3], hs = 0;
+        unsigned long long h[3];
         WRT_CUDA(cudaMemcpyAsync(h, &sub[j].wf->counters[WF_TOTAL_CLOSEST], sizeof h, cudaMemcpyDeviceToHost, st));
-        WRT_CUDA(cudaMemcpyAsync(&hs, &sub[j].wf->counters[WF_TOTAL_SUSP], sizeof hs, cudaMemcpyDeviceToHost, st));
         WRT_CUDA(cudaStreamSynchronize(st));
         sc->stats.closest_rays += h[0]; sc->stats.shadow_rays += h[1];
         sc->stats.extend_rays += h[0]; sc->stats.extend_launches += h[2];
-        sc->stats.suspended_rays += hs;
     }
     // stage times: sum of per-launch CUDA-event durations over all sub-pools (launches of different
     // sub-pools overlap, so the sums can exceed the wall time of the render)

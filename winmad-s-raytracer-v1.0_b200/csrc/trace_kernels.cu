@@ -40,7 +40,6 @@ struct ClosestSrc {
     const DevSceneView* sc;
     const wrt_ray* rays; int32_t* prim; float* t_out; float* p3; float* n3; int32_t* inside; int32_t* matid;
     static constexpr bool kCanDecide = false;
-    static constexpr bool kCanSuspend = false;
     __device__ __forceinline__ void target(size_t, float&, float&, float&) const {}
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
@@ -72,7 +71,6 @@ k_trace_closest(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, int
 struct AnySrc {
     const wrt_ray* rays; uint8_t* hit;
     static constexpr bool kCanDecide = false;
-    static constexpr bool kCanSuspend = false;
     __device__ __forceinline__ void target(size_t, float&, float&, float&) const {}
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
@@ -92,7 +90,6 @@ k_trace_any(DevSceneView sc, const wrt_ray* __restrict__ rays, size_t n, uint8_t
 struct ShadowTestSrc {
     const wrt_ray* rays; const float* target3; float* visible;
     static constexpr bool kCanDecide = true;      // scheduler 4: stop once the verdict can no longer change (occlusion_decided)
-    static constexpr bool kCanSuspend = false;
     __device__ __forceinline__ void target(size_t i, float& x, float& y, float& z) const { x = target3[3 * i]; y = target3[3 * i + 1]; z = target3[3 * i + 2]; }
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r) const { r = load_ray(rays, i); return true; }
@@ -116,7 +113,6 @@ struct OccludedSrc {
     const float* q9; uint8_t* occluded;
     float tx, ty, tz;
     static constexpr bool kCanDecide = true;
-    static constexpr bool kCanSuspend = false;
     __device__ __forceinline__ void target(size_t i, float& x, float& y, float& z) const { x = q9[9 * i + 6]; y = q9[9 * i + 7]; z = q9[9 * i + 8]; }
     __device__ __forceinline__ bool load(size_t i, RayIn& r)
     {

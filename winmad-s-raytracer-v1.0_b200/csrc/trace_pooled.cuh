@@ -50,6 +50,18 @@ constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 #ifndef WRT_COOP_MIN_RECORDS
 #define WRT_COOP_MIN_RECORDS 8
 #endif
+// The NODE work of those last rays is one dependent chain per ray, executed by a warp that has nothing else to issue: what it
+// costs is instructions, not memory latency (the longest C3 rays — 2 300 interior visits, 2 100 leaves of ~2 triangles — took
+// 3.78 ms alone, 400 ns per visit; prefetching the child pair into L1 changed nothing, profiles/r2_experiments.md).  Most of those
+// instructions were the two ring switches per leaf (store the state, re-queue, reload, cooperative pass, re-queue, reload).  In the
+// tail loop a node round therefore tests a SHORT leaf (< WRT_COOP_MIN_RECORDS records) right where it meets it — the same
+// leaf_record() steps in the same order — and runs WRT_TAIL_NODE_STEPS steps per ray instead of 6 (no other ray waits for the lanes).
+#ifndef WRT_TAIL_NODE_STEPS
+#define WRT_TAIL_NODE_STEPS 24
+#endif
+#ifndef WRT_TAIL_INLINE_LEAVES
+#define WRT_TAIL_INLINE_LEAVES 1
+#endif
 
 // Stack entries in the global scratch.  The reference pushes (far child, t, tmax) and, popping, restores all three
 // (KDtreeAccel.cpp:349-384).  tmax is redundant: it only ever changes in the push itself (tmax = t), so at any moment
@@ -71,23 +83,6 @@ struct PoolSmem {
 };
 
 constexpr size_t kPoolStackBytesPerWarp = (size_t)kPoolStack * kPoolRays * sizeof(float4);
-
-// Rays carried over to the NEXT launch of the same queue (work sources with Src::kCanSuspend, i.e. the path tracer's extend
-// kernel).  A launch ends when its longest ray ends, and on the scenes here a handful of rays are 30-50x longer than the mean
-// (grazing rays that pierce hundreds of leaves): ~3.5 ms of tail per launch on the 1 M-triangle scene, ~0.9 ms of a 0.9 ms
-// launch on torus.scene as shipped.  Once a warp is in its tail loop (work counter exhausted, <= WRT_COOP_RAYS rays left) it
-// serves them for at most Src::tail_budget() more rounds, then writes the complete traversal state of what is left — the 80
-// bytes of PoolSmem and rows 0..sp of the ray's stack — to a record and returns.  The work source marks the work item
-// (`suspended`), the wavefront re-queues it untouched, and the next launch's refill restores the record into a slot
-// (`resume_id`) and goes on exactly where the ray stopped: same state, same steps, same result — the traversal is only cut
-// into two launches, the long ray now runs beside the next launch's bulk instead of holding this launch open.
-struct SuspendBuf {
-    float4* state;             // [5][cap]: a b c d e of PoolSmem
-    float2* stack;             // [kPoolStack + 1][cap]: rows 0..sp of the 8-byte stack (row 0 = sentinel)
-    unsigned cap;
-};
-constexpr size_t suspend_state_bytes(unsigned cap) { return (size_t)5 * cap * sizeof(float4); }
-constexpr size_t suspend_stack_bytes(unsigned cap) { return (size_t)(kPoolStack + 1) * cap * sizeof(float2); }
 
 // One cooperative pass over the rest of a ray's leaf (see WRT_COOP_RAYS); only the tail loop (pooled_tail, out of line) calls it.
 // Returns true when the query was decided and consumed (boolean queries); otherwise the ray goes back to the node ring.
@@ -158,8 +153,6 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
     const unsigned RM = kPoolRays - 1;
     unsigned hn = R.hn, tn = R.tn, hp = R.hp, tp = R.tp, hf = R.hf, tf = R.tf;
     bool exhausted = TAIL;
-    unsigned rounds = 0u, budget = 0u;
-    if constexpr (TAIL && Src::kCanSuspend) budget = src.tail_budget();
 
     for (;;) {
         // ---- refill free slots from the global work counter ------------------------------------
@@ -175,31 +168,11 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                 unsigned slot = 0;
                 if (have) slot = sm.ring[2][(hf + k) & RM];
                 __syncwarp();
-                bool started = false, to_prim = false;
+                bool started = false;
                 const size_t item = (size_t)base + k;
                 if (have && item < n) {
-                    bool resumed = false;
-#if WRT_STACK8
-                    if constexpr (Src::kCanSuspend) {
-                        const int rid = src.resume_id(item);
-                        if (rid >= 0) {      // a ray suspended by the previous launch: restore its record into this slot
-                            const SuspendBuf sb = src.susp_in();
-                            const size_t c = sb.cap;
-                            sm.a[slot] = sb.state[0 * c + rid]; sm.b[slot] = sb.state[1 * c + rid]; sm.c[slot] = sb.state[2 * c + rid];
-                            const float4 d = sb.state[3 * c + rid];
-                            sm.d[slot] = d;
-                            float4 e4 = sb.state[4 * c + rid];
-                            const int rec = __float_as_int(e4.y), rec_end = __float_as_int(e4.z);
-                            sm.e[slot] = make_int4(__float_as_int(e4.x), rec, rec_end, (int)item);
-                            const int sp = __float_as_int(d.w) & 0xffff;
-                            float2* col = reinterpret_cast<float2*>(gstack) + slot;
-                            for (int q = 0; q <= sp; q++) col[(unsigned)q * (unsigned)kPoolRays] = sb.stack[(size_t)q * c + rid];
-                            started = true; resumed = true; to_prim = rec < rec_end;
-                        }
-                    }
-#endif
                     RayIn r;
-                    if (!resumed && src.load(item, r)) {
+                    if (src.load(item, r)) {
                         Trav T;
                         if (trav_begin(sc, r, T)) {
                             sm.a[slot] = make_float4(r.ox, r.oy, r.oz, r.dx);
@@ -214,14 +187,9 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                         } else src.done(item, r, -1, WRT_INF);
                     }
                 }
-                const unsigned bs = __ballot_sync(FULL, started && !to_prim);
-                if (started && !to_prim) sm.ring[0][(tn + __popc(bs & lt)) & RM] = (unsigned char)slot;
+                const unsigned bs = __ballot_sync(FULL, started);
+                if (started) sm.ring[0][(tn + __popc(bs & lt)) & RM] = (unsigned char)slot;
                 tn += __popc(bs);
-                if constexpr (Src::kCanSuspend) {
-                    const unsigned bp = __ballot_sync(FULL, started && to_prim);
-                    if (started && to_prim) sm.ring[1][(tp + __popc(bp & lt)) & RM] = (unsigned char)slot;
-                    tp += __popc(bp);
-                }
                 const unsigned bf = __ballot_sync(FULL, have && !started);
                 if (have && !started) sm.ring[2][(tf + __popc(bf & lt)) & RM] = (unsigned char)slot;
                 tf += __popc(bf);
@@ -235,36 +203,6 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
             continue;
         }
         if (!TAIL && WRT_COOP_RAYS > 0 && exhausted && cn + cp <= (unsigned)WRT_COOP_RAYS) break;     // the tail loop takes over
-#if WRT_STACK8
-        if constexpr (TAIL && Src::kCanSuspend) {
-            if (budget != 0u && ++rounds > budget) {
-                // ---- out of budget: what is left goes to the next launch (SuspendBuf above) -----------------------------
-                const unsigned cnt = cn + cp;                    // <= WRT_COOP_RAYS <= 32
-                const SuspendBuf sb = src.susp_out();
-                unsigned long long first = 0;
-                if (lane == 0) first = atomicAdd(src.susp_counter(), (unsigned long long)cnt);
-                first = __shfl_sync(FULL, first, 0);
-                if (first + cnt <= (unsigned long long)sb.cap) {
-                    if (lane < cnt) {
-                        const unsigned slot = lane < cn ? sm.ring[0][(hn + lane) & RM] : sm.ring[1][(hp + (lane - cn)) & RM];
-                        const size_t c = sb.cap, id = (size_t)first + lane;
-                        const float4 d = sm.d[slot];
-                        const int4 e = sm.e[slot];
-                        sb.state[0 * c + id] = sm.a[slot]; sb.state[1 * c + id] = sm.b[slot]; sb.state[2 * c + id] = sm.c[slot];
-                        sb.state[3 * c + id] = d;
-                        sb.state[4 * c + id] = make_float4(__int_as_float(e.x), __int_as_float(e.y), __int_as_float(e.z), 0.f);
-                        const int sp = __float_as_int(d.w) & 0xffff;
-                        const float2* col = reinterpret_cast<const float2*>(gstack) + slot;
-                        for (int q = 0; q <= sp; q++) sb.stack[(size_t)q * c + id] = col[(unsigned)q * (unsigned)kPoolRays];
-                        src.suspended((size_t)(unsigned)e.w, (unsigned)id);
-                    }
-                    hn = tn; hp = tp;
-                    break;
-                }
-                budget = 0u;       // the record buffer is full: finish these rays here
-            }
-        }
-#endif
         // (a ray with a short rest of a leaf is served as well by the ordinary primitive round, which takes all waiting rays at once)
         if (TAIL && cp > 0 && (cp == 1u || sm.e[sm.ring[1][hp & RM]].z - sm.e[sm.ring[1][hp & RM]].y >= WRT_COOP_MIN_RECORDS)) {
             // ---- cooperative leaf pass (tail of the launch): the whole warp works on the FIRST ray of the prim ring --------
@@ -357,7 +295,7 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                 //  of the child pair right after the node header is known -19 % / -42 % for one / both children, of a
                 //  leaf's first records on leaf entry -4 %; a warp-uniform loop with a `live` flag instead of the breaks -4 %:
                 //  profiles/r1_experiments.md)
-                for (int s = 0; s < kNodeSteps; s++) {
+                for (int s = 0; s < (TAIL ? WRT_TAIL_NODE_STEPS : kNodeSteps); s++) {
                     if (need_pop) {
                         need_pop = false;
                         if (T.sp <= 0) { next = 2; break; }
@@ -383,7 +321,22 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                     const unsigned hi = packed >> 2;                  // child pair (interior) | record count (leaf)
                     const bool leaf = (packed & 3u) == WRT_LEAF_TAG;
                     if (skip || (leaf && hi == 0u)) { need_pop = true; continue; }
-                    if (leaf) { leaf_first = __float_as_int(na.x); leaf_end = leaf_first + (int)hi; next = 1; break; }
+                    if (leaf) {
+                        if (TAIL && WRT_TAIL_INLINE_LEAVES && hi < (unsigned)WRT_COOP_MIN_RECORDS) {      // short leaf, tail loop: tested here
+                            int rec = __float_as_int(na.x);
+                            const int end = rec + (int)hi;
+                            const float best0 = T.best;
+                            while (rec < end) rec += leaf_record<PRUNED>(sc, rec, r, T);
+                            if (Src::kCanDecide && T.best < best0) {
+                                float tx, ty, tz;
+                                src.target((size_t)(unsigned)sm.e[slot].w, tx, ty, tz);
+                                if (occlusion_decided(r, T.best, tx, ty, tz)) { next = 2; break; }
+                            }
+                            need_pop = true;
+                            continue;
+                        }
+                        leaf_first = __float_as_int(na.x); leaf_end = leaf_first + (int)hi; next = 1; break;
+                    }
                     // interior step (trav_interior, KDtreeAccel.cpp:325-358) without branches; the push goes to the
                     // global scratch stack
                     const int axis = (int)(packed & 3u);
@@ -411,6 +364,7 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                 } else {
                     sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(T.node), __int_as_float(T.sp | (T.degen ? (1 << 29) : 0) | (need_pop ? (1 << 30) : 0)));
                     if (next == 1) { sm.e[slot].y = leaf_first; sm.e[slot].z = leaf_end; }
+                    if (TAIL && WRT_TAIL_INLINE_LEAVES) { sm.c[slot].w = T.best; sm.e[slot].x = T.res; }      // (leaves tested in this round)
                 }
             }
             const unsigned b0 = __ballot_sync(FULL, have && next == 0);

@@ -22,10 +22,8 @@ enum {
     WF_AUX2_COUNT = 7,  // BDPT: BSDF-sampled rays traced by the DI kernel
     WF_WORK4 = 8,       // BDPT DI kernel work fetch
     WF_CV_COUNT = 9,    // BDPT: camera-vertex records written by the camera shade kernel for the connection kernel
-    WF_SUSP_COUNT = 10, // PT: rays the extend kernel of this iteration suspended (trace_pooled.cuh, SuspendBuf)
     WF_PAIR_COUNT = 11, // BDPT: (camera vertex, light vertex) pairs listed for the connection kernel
-    WF_RES_COUNT = 12,  // PT: entries of the priority run of the next queue: paths whose ray the extend kernel suspended (resumed FIRST by the next launch)
-    WF_BANK = 16,
+    WF_BANK = 12,
     // ---- persistent part, after the two banks ----
     WF_PERSIST = 2 * WF_BANK,
     WF_NEXT_SAMPLE = WF_PERSIST + 0, // next camera sample to hand out (path regeneration)
@@ -33,13 +31,11 @@ enum {
     WF_TOTAL_SHADOW = WF_PERSIST + 2,  // queries traced by the shadow / DI kernels
     WF_TOTAL_ITERS = WF_PERSIST + 3,   // iterations that had work
     WF_VISITS = WF_PERSIST + 4,     // +0 inner, +1 leaf, +2 tri, +3 sphere (counting mode)
-    WF_TOTAL_SUSP = WF_PERSIST + 8,   // rays handed over to a next launch (ray suspension)
-    WF_COUNTERS = WF_PERSIST + 9
+    WF_COUNTERS = WF_PERSIST + 8
 };
 
-// Length of the queue an iteration consumes: resumed rays (their own short list, work items [0, n_res)), then regenerated camera
-// rays (back of the queue array), then continuing paths (front).
-__host__ __device__ inline size_t wf_queue_n(const unsigned long long* prev) { return (size_t)(prev[WF_RES_COUNT] + prev[WF_NEXT_COUNT] + prev[WF_GEN_COUNT]); }
+// Length of the queue an iteration consumes: continuing paths (front of the queue) + regenerated camera rays (back).
+__host__ __device__ inline size_t wf_queue_n(const unsigned long long* prev) { return (size_t)(prev[WF_NEXT_COUNT] + prev[WF_GEN_COUNT]); }
 
 struct PathPool {            // SoA over `capacity` slots
     wrt_ray* ray;            // 32 B, float4-aligned
@@ -81,9 +77,6 @@ struct wrt_wavefront {
     void* trav_scratch2; size_t trav_scratch2_bytes;
     cudaStream_t shadow_stream;
     cudaEvent_t shaded_ev[2], shadowed_ev[2];
-    // PT: records of rays an extend launch hands over to the next one (trace_pooled.cuh, SuspendBuf); two sets, iteration parity
-    void* susp_state[2]; void* susp_stack[2]; unsigned susp_cap;
-    uint32_t* resq[2];                  // the priority run of the queue (path slots to resume), by iteration parity like queue[]
 };
 
 #include <functional>

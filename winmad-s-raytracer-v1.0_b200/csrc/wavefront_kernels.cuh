@@ -53,38 +53,15 @@ __device__ __forceinline__ uint32_t queue_slot(const uint32_t* queue, size_t e, 
     return e < n_gen ? WRT_LDSU(queue + (cap - 1 - e)) : WRT_LDSU(queue + (e - n_gen));
 }
 
-// Ray suspension (trace_pooled.cuh, SuspendBuf): the extend kernel marks a suspended ray's path with hit_prim = -2 - record id; the
-// path tracer's shade kernel leaves such a path untouched and lists its slot in the PRIORITY run of the next queue (`resq`, work
-// items [0, n_res)), so the next extend launch resumes it first and the long ray runs beside the whole of that launch.  (Listed
-// among the ordinary entries it was picked up late, ran into the next tail and was handed on again and again: measured slower
-// than no suspension at all, profiles/r2_experiments.md.)  Off (budget 0, no lists) for the BDPT / Whitted wavefronts and the
-// counting kernels.
-constexpr size_t kSuspendMinQueue = 8192;
-struct ExtendSuspend {
-    SuspendBuf in, out;            // records written by the previous launch / by this one (two buffers, iteration parity)
-    unsigned long long* counter;   // records written by this launch
-    unsigned budget;               // tail rounds before a warp suspends what it has left; 0 = never
-    const uint32_t* resq;          // priority run of this launch's queue
-};
-
 struct ExtendSrc {
-    PathPool pool; const uint32_t* queue; size_t n_res, n_gen, cap;
-    ExtendSuspend sus;
+    PathPool pool; const uint32_t* queue; size_t n_gen, cap;
     static constexpr bool kCanDecide = false;
-    static constexpr bool kCanSuspend = true;
-    __device__ __forceinline__ uint32_t slot_of(size_t e) const { return e < n_res ? sus.resq[e] : queue_slot(queue, e - n_res, n_gen, cap); }
-    __device__ __forceinline__ unsigned tail_budget() const { return sus.budget; }
-    __device__ __forceinline__ const SuspendBuf& susp_in() const { return sus.in; }
-    __device__ __forceinline__ const SuspendBuf& susp_out() const { return sus.out; }
-    __device__ __forceinline__ unsigned long long* susp_counter() const { return sus.counter; }
-    __device__ __forceinline__ int resume_id(size_t e) const { return e < n_res ? -2 - pool.hit_prim[sus.resq[e]] : -1; }
-    __device__ __forceinline__ void suspended(size_t e, unsigned id) const { pool.hit_prim[slot_of(e)] = -2 - (int)id; }
     __device__ __forceinline__ void target(size_t, float&, float&, float&) const {}
     __device__ __forceinline__ bool decided(const RayIn&, float) const { return false; }
-    __device__ __forceinline__ bool load(size_t e, RayIn& r) const { r = pool_load_ray(pool, slot_of(e)); return true; }
+    __device__ __forceinline__ bool load(size_t e, RayIn& r) const { r = pool_load_ray(pool, queue_slot(queue, e, n_gen, cap)); return true; }
     __device__ __forceinline__ void done(size_t e, const RayIn&, int prim, float t) const
     {
-        const uint32_t slot = slot_of(e);
+        const uint32_t slot = queue_slot(queue, e, n_gen, cap);
         WRT_STS(pool.hit_prim + slot, prim);
         WRT_STS(pool.hit_t + slot, t);
     }
@@ -98,17 +75,13 @@ __device__ __forceinline__ const unsigned long long* wf_prev(const unsigned long
 template <bool PRUNED>
 __global__ void __launch_bounds__(kBlock, WRT_MIN_BLOCKS)
 k_pt_extend(DevSceneView sc, PathPool pool, const uint32_t* __restrict__ queue, unsigned long long* ctr, int parity,
-            float4* scratch, size_t cap, ExtendSuspend sus)
+            float4* scratch, size_t cap)
 {
     const unsigned long long* prev = wf_prev(ctr, parity);
-    const size_t n = wf_queue_n(prev), n_gen = (size_t)prev[WF_GEN_COUNT], n_res = (size_t)prev[WF_RES_COUNT];
+    const size_t n = wf_queue_n(prev), n_gen = (size_t)prev[WF_GEN_COUNT];
     if (n == 0) return;
-    // (resumed rays were counted by the launch that started them)
-    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr[WF_TOTAL_CLOSEST], (unsigned long long)(n - n_res)); atomicAdd(&ctr[WF_TOTAL_ITERS], 1ull); }
-    // a queue this short is the end of the frame: nothing is left to run beside a suspended ray, finish everything here
-    if (n < kSuspendMinQueue) sus.budget = 0u;
-    sus.counter = &wf_cur(ctr, parity)[WF_SUSP_COUNT];
-    ExtendSrc src = { pool, queue, n_res, n_gen, cap, sus };
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(&ctr[WF_TOTAL_CLOSEST], (unsigned long long)n); atomicAdd(&ctr[WF_TOTAL_ITERS], 1ull); }
+    ExtendSrc src = { pool, queue, n_gen, cap };
     trace_rays<PRUNED>(sc, src, &wf_cur(ctr, parity)[WF_WORK], n, scratch);
 }
 
@@ -175,7 +148,6 @@ struct ShadowSrc {
     ShadowQueue sq; float* film; float scale;
     float tx, ty, tz;     // target point of the query this lane is tracing (scheduler 2: one ray per lane)
     static constexpr bool kCanDecide = true;
-    static constexpr bool kCanSuspend = false;
     __device__ __forceinline__ void target(size_t e, float& x, float& y, float& z) const { const float4 c = WRT_LDS4(sq.c + e); x = c.x; y = c.y; z = c.z; }
     __device__ __forceinline__ bool load(size_t e, RayIn& r)
     {
