@@ -546,19 +546,27 @@ def main():
                                     "note": "SURVEY 8(d): bytes of the reference's FULL traversal (no early exit) of the same rays / this kernel's time; "
                                             "a ratio above 1 is work avoided by the bit-exact pruning, not bandwidth"}}
     elif w["integrator"] == "bdpt" and shade_ms > 0:
-        # C4: 38 primitives — traversal is a handful of steps; the dominant kernels are the shade kernels (camera vertices connect to
-        # every stored light vertex), which stream path state and light vertices from HBM: a memory roofline.
+        # C4: 38 primitives — traversal is a handful of steps per ray; the dominant kernels are the per-vertex kernels (camera shade,
+        # the (camera vertex, light vertex) connection kernel, light shade).  The committed ncu capture of the connection kernel says
+        # what binds them: issue slots and divergence (two BSDF set-ups with IEEE divisions and one powf per pair), DRAM far from peak.
+        # `achieved` keeps the HBM yardstick every line of this bench uses: algorithmic bytes of those kernels / their launch durations.
         per_step_closest, per_step_shadow = closest_rays / args.steps, shadow_rays / args.steps
-        bytes_step = per_step_closest * (32 + 16 + 16 + 4 + 8 + 72) + per_step_shadow * (64 + 52 + 52)
+        bytes_step = per_step_closest * (32 + 16 + 16 + 4 + 8 + 72) + per_step_shadow * (64 + 80 + 4 + 52 + 52)
         ach = bytes_step * args.steps / (shade_ms * 1e-3) / 1e9
         line["roofline"] = {
-            "bound": "hbm", "kernel": "k_bdpt_camera_shade + k_bdpt_light_shade", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "bound": "issue", "kernel": "k_bdpt_connect + k_bdpt_camera_shade + k_bdpt_light_shade", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "peak_source": peak_src,
-            "what": "algorithmic bytes of the shade kernels: per path vertex 76 B of state read + 72 B written; per connection 64 B light vertex read, "
-                    "52 B queue entry written and 52 B read back by the connection kernel / summed CUDA-event durations of the shade launches",
+            "what": "algorithmic bytes of the per-vertex kernels: per path vertex 76 B of state read + 72 B written; per connection 64 B light vertex + 80 B "
+                    "camera record + 4 B pair entry read, 52 B queue entry written and 52 B read back by the occlusion kernel / summed CUDA-event durations "
+                    "of those launches; against the measured HBM copy peak as the common yardstick — the binding limit is the issue rate: see `issue`",
             "avg_launch_ms": shade_ms / max(ext_launches, 1), "launches": int(ext_launches),
-            "kernel_share_of_step": shade_ms / ms, "traffic": None,
-            "stage_ms_per_step": {"extend": ext_ms / args.steps, "shade": shade_ms / args.steps, "connect+di": shadow_ms / args.steps},
+            "kernel_share_of_step": shade_ms / ms,
+            "traffic": (nm.get("dram_bytes_per_launch") or None),
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of one k_bdpt_connect launch (%s)" % nm.get("source", "none"),
+            "issue": {"issue_active_pct": nm.get("issue_active_pct"), "threads_per_inst": nm.get("threads_per_inst"),
+                      "useful_issue_frac": (nm["issue_active_pct"] / 100.0 * nm["threads_per_inst"] / 32.0) if nm.get("issue_active_pct") and nm.get("threads_per_inst") else None,
+                      "source": nm.get("source")},
+            "stage_ms_per_step": {"extend": ext_ms / args.steps, "shade+connect": shade_ms / args.steps, "occlusion+di": shadow_ms / args.steps},
             "traversal_own_work": {"visits_per_ray": visits_k, "bytes_per_ray": b_ray_k}}
     else:
         line["roofline"] = None
