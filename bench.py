@@ -52,13 +52,6 @@ WORKLOADS = {
 }
 
 
-# DRAM bytes per ray of k_pt_extend from the committed ncu captures (profiles/r1_final_launches_and_ncu.md: C3, one
-# 33 554 432-ray launch, dram__bytes_read.sum 4.749 GB + dram__bytes_write.sum 1.546 GB; profiles/r1_ncu_extend_c5.md: C5,
-# one 33 554 432-ray launch, 22.52 GB + 4.88 GB).
-NCU_DRAM_BYTES_PER_RAY = {"c3": (4.749402e9 + 1.546372e9) / 33554432.0, "c5": (22.523734e9 + 4.877666e9) / 33554432.0}
-NCU_SOURCE = {"c3": "profiles/r1_final_launches_and_ncu.md", "c5": "profiles/r1_ncu_extend_c5.md"}
-
-
 def ncu_metrics(workload):
     """Counters of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/ncu_metrics.json,
     written by tools/ncu_summary.py from the .ncu-rep of the same command): DRAM bytes per ray, issue-slot utilisation,
@@ -293,8 +286,10 @@ def main():
 
     t0 = time.time()
     sc = make_scene(w)
+    scene_gen_s = time.time() - t0          # synthetic geometry (numpy) or fixture load: not part of the library
+    t0 = time.time()
     hs = util.host_scene(W, sc)
-    kd_build_s = time.time() - t0
+    kd_build_s = time.time() - t0           # HostScene from arrays incl. the exact multi-threaded KD build (host/kd_build.cpp)
     t0 = time.time()
     scene = W.Scene(hs)
     upload_s = time.time() - t0
@@ -495,7 +490,7 @@ def main():
                    "l2": "inputs larger than L2: the path pool (up to 2^26 slots x 176 B in concurrent sub-pools) is rewritten every bounce; the scene is meant to stay L2-resident",
                    "loop": "device-driven: every iteration reads its queue length from the counter bank its predecessor wrote; the host enqueues iterations "
                            "back to back and polls one batch late (pt_wavefront.cu)",
-                   "prims": int(sc.n_prims), "kd_build_s": round(kd_build_s, 2), "upload_s": round(upload_s, 2)},
+                   "prims": int(sc.n_prims), "scene_gen_s": round(scene_gen_s, 2), "kd_build_s": round(kd_build_s, 2), "upload_s": round(upload_s, 2)},
         "samples_per_s": total_samples / (ms / 1e3), "rays_per_sample": rays / total_samples,
         "mean_radiance": mean_radiance,
         "gpu_launches": launches,

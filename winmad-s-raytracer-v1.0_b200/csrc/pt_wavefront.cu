@@ -415,6 +415,9 @@ static void pt_plan(const PtParams& P, PtPlan& plan, bool whitted = false)
     total = std::max<unsigned long long>(total, 1024ull);
     int k = sub_pools();
     if (total < (1ull << 18)) k = 1;
+    // Whitted: the pool is capped at 2^23 slots (pending lists), so halving it makes the launches small: one sub-pool measured
+    // 1094 Mrays/s against 862 (two) and 737 (four) on torus.scene (profiles/r2_experiments.md)
+    if (whitted && !getenv("WRT_SUBPOOLS")) k = 1;
     plan.k = k;
     // Sub-pool sizes.  When the pool holds the whole frame (no slot is ever regenerated: a frame of <= 2^26 samples, e.g. one
     // GPU's share of a sharded render) every sub-pool runs the same short chain of iterations — one large launch of camera
