@@ -213,6 +213,16 @@ def test_warpsim_schedulers_match_port(wrt, monkeypatch, sched):
     full = port.intersect(rays, full=True)
     q = scenes.nee_queries(full[2], (full[0] >= 0) & (full[5] > 0), sc.lights)[:n]
     assert np.array_equal(ws.trace_occluded(q, True, sched), port.occluded(q))
+    if sched == 3:
+        # small launches (fewer rays than pool slots: even-share refill, tail loop entered with up to 16 rays, per-ray lane groups
+        # of 2 ... 32 lanes in the leaves): closest hits and occlusion flags
+        occ = port.occluded(q)
+        want_r = port.intersect(rays)
+        for m in (3, 7, 40, 100, 230):
+            for pruned in (True, False):
+                got = ws.trace_closest(rays[:m], pruned, 3)
+                assert np.array_equal(got[0], want_r[0][:m]) and np.array_equal(util.bits(got[1]), util.bits(want_r[1][:m])), (m, pruned)
+            assert np.array_equal(ws.trace_occluded(q[:m], True, 3), occ[:m]), m
     # golden primary rays of the fixture (a strided sample): the reference's own answers
     cam = wrt.Camera.from_ref_array(z["cam45"])
     prim_rays = wrt.generate_rays(cam, scenes.pixel_centres(512, 512, step=2))

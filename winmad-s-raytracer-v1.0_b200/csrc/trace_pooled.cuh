@@ -42,8 +42,10 @@ constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 #endif
 // Tail of a launch: once the global work counter is exhausted and a warp is down to its last rays, those are the rays that
 // decide when the launch ends — and on the scenes here they are long because of LEAF work (torus.scene: mean 20, p99.9 1300,
-// max 1500 primitive tests per ray).  With at most WRT_COOP_RAYS rays waiting for primitive tests the warp stops giving one lane
-// to one ray and tests 32 records of ONE ray per pass instead (coop_leaf below).
+// max 1500 primitive tests per ray).  With at most WRT_COOP_RAYS rays left the warp enters the tail loop, which stops giving one lane
+// to one ray: every ray inside a leaf gets a group of 32 / pow2ceil(rays) lanes that test as many records per pass (group_leaf_pass
+// below).  A SMALL launch (fewer work items than pool slots on the device, `share` below) enters it with up to 16 rays: its warps
+// are never full anyway, and 2 - 32 records per ray and pass beat 4 in sequence (torus.scene as shipped: 76 k rays per launch).
 #ifndef WRT_COOP_RAYS
 #define WRT_COOP_RAYS 4
 #endif
@@ -56,6 +58,9 @@ constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 // instructions were the two ring switches per leaf (store the state, re-queue, reload, cooperative pass, re-queue, reload).  In the
 // tail loop a node round therefore tests a SHORT leaf (< WRT_COOP_MIN_RECORDS records) right where it meets it — the same
 // leaf_record() steps in the same order — and runs WRT_TAIL_NODE_STEPS steps per ray instead of 6 (no other ray waits for the lanes).
+#ifndef WRT_MIN_SHARE
+#define WRT_MIN_SHARE 8
+#endif
 #ifndef WRT_TAIL_NODE_STEPS
 #define WRT_TAIL_NODE_STEPS 24
 #endif
@@ -84,24 +89,34 @@ struct PoolSmem {
 
 constexpr size_t kPoolStackBytesPerWarp = (size_t)kPoolStack * kPoolRays * sizeof(float4);
 
-// One cooperative pass over the rest of a ray's leaf (see WRT_COOP_RAYS); only the tail loop (pooled_tail, out of line) calls it.
-// Returns true when the query was decided and consumed (boolean queries); otherwise the ray goes back to the node ring.
+// Cooperative leaf passes of the tail loop (pooled_tail, out of line): with cnt <= 16 rays waiting for primitive tests the warp gives
+// every ray a GROUP of G = 32 / pow2ceil(cnt) lanes (one ray: the whole warp).  Lane j of a group tests record rec + j of its ray's
+// leaf (Triangle::hit / Sphere::hit with their exact arithmetic; skip records are no-ops: every primitive of the leaf is tested, as
+// the reference does), then the hits are offered to the acceptance rule `t - best < -EPS` in RECORD ORDER (KDtreeAccel.cpp:363-373)
+// — the same fold the sequential loop performs, so res / best come out identical.  Up to WRT_GROUP_PASSES passes per call.
+// Returns, per lane, what became of its group's ray: 0 = still in the leaf, 1 = leaf done (back to the node ring), 2 = decided and
+// consumed (boolean queries), 3 = lane has no ray.  The group's leader (j == 0) has written the state back.
+#ifndef WRT_GROUP_PASSES
+#define WRT_GROUP_PASSES 4
+#endif
 template <class Src>
-__device__ __forceinline__ bool coop_leaf(const DevSceneView& sc, Src& src, PoolSmem& sm, unsigned slot, unsigned lane)
+__device__ __forceinline__ int group_leaf_pass(const DevSceneView& sc, Src& src, PoolSmem& sm, unsigned slot, bool have, unsigned lane, unsigned lgG)
 {
     const unsigned FULL = 0xffffffffu;
+    const unsigned G = 1u << lgG, j = lane & (G - 1u), first = lane & ~(G - 1u);
+    const unsigned gmask = G == 32u ? FULL : ((1u << G) - 1u);
     const float4 a = sm.a[slot], b = sm.b[slot];
     RayIn r; r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
     const int4 e = sm.e[slot];
     float best = sm.c[slot].w;
-    int res = e.x;
+    int res = e.x, rec = e.y;
     bool decided = false;
-    for (int base = e.y; base < e.z && !decided; base += 32) {
-        const int my = base + (int)lane;
+    for (int p = 0; p < WRT_GROUP_PASSES; p++) {
+        const int my = rec + (int)j;
         bool hit = false; float t = 0.f; int prim = -1;
-        if (my < e.z) {
-            const float4* rec = sc.leaf_recs + 3 * (size_t)my;
-            const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+        if (have && !decided && my < e.z) {
+            const float4* rp = sc.leaf_recs + 3 * (size_t)my;
+            const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
             const int kind = __float_as_int(r2.w);
             if (kind == 0) hit = triangle_t(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, t);
             else if (kind == 1) {
@@ -111,37 +126,41 @@ __device__ __forceinline__ bool coop_leaf(const DevSceneView& sc, Src& src, Pool
             }
             prim = __float_as_int(r0.w);
         }
-        unsigned m = __ballot_sync(FULL, hit);
+        unsigned m = (__ballot_sync(FULL, hit) >> first) & gmask;      // this group's hits, bit i = record rec + i
         const float best0 = best;
-        while (m) {
-            const int i = __ffs(m) - 1;
+        while (__any_sync(FULL, m != 0u)) {
+            const unsigned i = m ? (unsigned)__ffs(m) - 1u : 0u;
+            const float ti = __shfl_sync(FULL, t, first + i);
+            const int pi = __shfl_sync(FULL, prim, first + i);
+            if (m && (ti - best < -WRT_EPS)) { best = ti; res = pi; }
             m &= m - 1u;
-            const float ti = __shfl_sync(FULL, t, i);
-            const int pi = __shfl_sync(FULL, prim, i);
-            if (ti - best < -WRT_EPS) { best = ti; res = pi; }
         }
-        if (Src::kCanDecide && best < best0) {
+        rec += (int)G;
+        if (Src::kCanDecide && have && !decided && best < best0) {
             float tx, ty, tz;
             src.target((size_t)(unsigned)e.w, tx, ty, tz);
             decided = occlusion_decided(r, best, tx, ty, tz);
         }
+        if (!__any_sync(FULL, have && !decided && rec < e.z)) break;
     }
-    if (lane == 0) {
+    if (!have) return 3;
+    const bool leaf_done = rec >= e.z;
+    if (j == 0u) {
         if (decided) src.done((size_t)(unsigned)e.w, r, res, best);
         else {
             sm.c[slot].w = best;
-            sm.e[slot].x = res; sm.e[slot].y = e.z;
-            sm.d[slot].w = __int_as_float(__float_as_int(sm.d[slot].w) | (1 << 30));     // need_pop
+            sm.e[slot].x = res; sm.e[slot].y = leaf_done ? e.z : rec;
+            if (leaf_done) sm.d[slot].w = __int_as_float(__float_as_int(sm.d[slot].w) | (1 << 30));     // need_pop
         }
     }
-    return decided;
+    return decided ? 2 : (leaf_done ? 1 : 0);
 }
 
 struct PoolRings { unsigned hn, tn, hp, tp, hf, tf; };     // ring heads / tails (monotonic), warp-uniform
 
 // The scheduler loop.  TAIL = false: the steady state described at the top of this file; it returns as soon as the global
 // work counter is exhausted and at most WRT_COOP_RAYS rays are left in the pool.  TAIL = true: finishes those last rays —
-// same node rounds, but rays waiting for primitive tests get the cooperative leaf pass (coop_leaf).  Two instantiations, so
+// longer node rounds with short leaves tested in place, and cooperative leaf passes (group_leaf_pass).  Two instantiations, so
 // that the tail's code and registers stay out of the steady-state loop.
 template <bool PRUNED, bool TAIL, class Src>
 __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, unsigned long long* counter, size_t n,
@@ -153,11 +172,26 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
     const unsigned RM = kPoolRays - 1;
     unsigned hn = R.hn, tn = R.tn, hp = R.hp, tp = R.tp, hf = R.hf, tf = R.tf;
     bool exhausted = TAIL;
+    unsigned share = (unsigned)kPoolRays;
+#if !defined(WRT_WARPSIM_FIXED_SHARE)
+    if (!TAIL) {
+        const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+        const size_t even = (n + warps - 1) / warps;
+        if (even < (size_t)kPoolRays) share = even < (size_t)WRT_MIN_SHARE ? (unsigned)WRT_MIN_SHARE : (unsigned)even;
+    }
+#endif
 
     for (;;) {
         // ---- refill free slots from the global work counter ------------------------------------
         unsigned nfree = tf - hf;
-        if (!TAIL && !exhausted && nfree >= kMinRefill) {
+        // Small launches (fewer work items than pool slots on the device): a warp only fills its even SHARE of the launch
+        // (`share`, >= WRT_MIN_SHARE of its 64 slots) and refills when half of that is free, so that the rays of an expensive image
+        // region are spread over all resident warps instead of 64 to a warp (torus.scene as shipped: 76 k rays per launch on 5 328 warps).
+        if (share < (unsigned)kPoolRays) {
+            const unsigned used = (unsigned)kPoolRays - nfree;
+            nfree = used + (share + 1u) / 2u <= share ? share - used : 0u;
+        }
+        if (!TAIL && !exhausted && nfree >= (share < (unsigned)kPoolRays ? 1u : kMinRefill)) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(counter, (unsigned long long)nfree);
             base = __shfl_sync(FULL, base, 0);
@@ -202,20 +236,30 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
             if (exhausted) break;
             continue;
         }
-        if (!TAIL && WRT_COOP_RAYS > 0 && exhausted && cn + cp <= (unsigned)WRT_COOP_RAYS) break;     // the tail loop takes over
-        // (a ray with a short rest of a leaf is served as well by the ordinary primitive round, which takes all waiting rays at once)
-        if (TAIL && cp > 0 && (cp == 1u || sm.e[sm.ring[1][hp & RM]].z - sm.e[sm.ring[1][hp & RM]].y >= WRT_COOP_MIN_RECORDS)) {
-            // ---- cooperative leaf pass (tail of the launch): the whole warp works on the FIRST ray of the prim ring --------
-            // Lane l tests record rec + l of the ray's leaf (Triangle::hit / Sphere::hit with their exact arithmetic, skip records
-            // are no-ops: every primitive of the leaf is tested, as the reference does), then the hits are offered to the
-            // acceptance rule `t - best < -EPS` in RECORD ORDER (KDtreeAccel.cpp:363-373) — the same fold the sequential loop
-            // performs, so res / best come out identical.
-            const unsigned slot = sm.ring[1][hp & RM];
-            hp += 1;
+        if (!TAIL && WRT_COOP_RAYS > 0 && exhausted && cn + cp <= (share < (unsigned)kPoolRays ? 16u : (unsigned)WRT_COOP_RAYS)) break;     // the tail loop takes over
+        if (TAIL && cp > 0u && cp >= cn && cp <= 16u) {
+            // ---- cooperative leaf passes (tail loop): every ray of the prim ring gets a group of lanes (group_leaf_pass) --------
+            const unsigned cnt = cp;
+            const unsigned lgG = cnt <= 1u ? 5u : (cnt <= 2u ? 4u : (cnt <= 4u ? 3u : (cnt <= 8u ? 2u : 1u)));
+            const unsigned g = lane >> lgG;
+            const bool have = g < cnt;
+            unsigned slot = 0;
+            if (have) slot = sm.ring[1][(hp + g) & RM];
+            hp += cnt;
             __syncwarp();
-            const bool decided = coop_leaf(sc, src, sm, slot, lane);
-            if (lane == 0) sm.ring[decided ? 2 : 0][(decided ? tf : tn) & RM] = (unsigned char)slot;
-            if (decided) tf += 1; else tn += 1;
+            const int what = group_leaf_pass(sc, src, sm, slot, have, lane, lgG);
+            const bool leader = have && (lane & ((1u << lgG) - 1u)) == 0u;
+            const unsigned b1 = __ballot_sync(FULL, leader && what == 0);
+            if (leader && what == 0) sm.ring[1][(tp + __popc(b1 & lt)) & RM] = (unsigned char)slot;
+            tp += __popc(b1);
+            const unsigned b0 = __ballot_sync(FULL, leader && what == 1);
+            if (leader && what == 1) sm.ring[0][(tn + __popc(b0 & lt)) & RM] = (unsigned char)slot;
+            tn += __popc(b0);
+            if (Src::kCanDecide) {
+                const unsigned b2 = __ballot_sync(FULL, leader && what == 2);
+                if (leader && what == 2) sm.ring[2][(tf + __popc(b2 & lt)) & RM] = (unsigned char)slot;
+                tf += __popc(b2);
+            }
             __syncwarp();
             continue;
         }
