@@ -58,6 +58,38 @@ def test_parallel_kd_build_equals_serial(wrt, monkeypatch):
         assert np.array_equal(util.bits(a["root_box"]), util.bits(b["root_box"]))
 
 
+def _eps_dense_scene(n=64, scale=0.004):
+    """A mesh whose box bounds lie closer together than the reference's EPS (1e-3): the displaced torus scaled down until a triangle is
+    ~1e-4 across.  Long chains of event positions are then pairwise "equal" under cmp(), the comparator is as non-transitive as it gets,
+    and the sorted order is whatever the sorting ALGORITHM makes of it — the case the exact restatement of glibc's merge sort exists for."""
+    sc = scenes.synthetic_torus_scene(n=n, width=64, height=64, n_spheres=0)
+    sc.data = (sc.data.astype(np.float64) * scale).astype(np.float32)
+    return sc
+
+
+def test_parallel_sort_and_split_search_on_epsilon_dense_events(wrt, have_ref, monkeypatch):
+    """Events denser than EPS: the multi-threaded build (merge-sort restatement on threads, findSplitPlane over per-range prefix-minima
+    staircases, counted distribution) == the serial build with libc qsort == the reference's own tree."""
+    sc = _eps_dense_scene()
+    ext = sc.data.reshape(-1, 3)[: -6]
+    assert np.ptp(ext[:, 0]) / len(sc.data) ** 0.5 < 1e-3            # mean spacing of the bounds well below EPS
+    monkeypatch.setenv("WRT_KD_THREADS", "1")
+    a = util.host_scene(wrt, sc).arrays()["tree"]
+    monkeypatch.setenv("WRT_KD_CHUNK_MIN", "4000"); monkeypatch.setenv("WRT_KD_SORT_MIN", "1000")
+    for threads, sort in (("8", ""), ("5", ""), ("8", "libc")):
+        monkeypatch.setenv("WRT_KD_THREADS", threads); monkeypatch.setenv("WRT_KD_SORT", sort)
+        b = util.host_scene(wrt, sc).arrays()["tree"]
+        for k in ("axis", "left", "right", "first_ref", "nref", "refs"):
+            assert np.array_equal(a[k], b[k]), (threads, sort, k)
+        assert np.array_equal(util.bits(a["split"]), util.bits(b["split"]))
+    if have_ref:
+        r = util.ref_scene(sc).tree()
+        for k in ("axis", "left", "right", "nref", "refs"):
+            assert np.array_equal(a[k], r[k]), k
+        inner = r["axis"] >= 0
+        assert np.array_equal(util.bits(a["split"][inner]), util.bits(r["split"][inner]))
+
+
 def test_scene_loader_matches_reference(wrt, have_ref):
     """Our XML/OBJ loader vs Scene::loadScene on torus.scene (needs /root/reference: build container only)."""
     from oracle import refpy

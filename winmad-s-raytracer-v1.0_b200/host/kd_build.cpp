@@ -215,7 +215,9 @@ bool libc_qsort_is_msort()
 void sort_events(std::vector<Event>& e, int threads)
 {
     const char* force = getenv("WRT_KD_SORT");      // "libc": always libc qsort (the tests compare the two)
-    if (threads <= 1 || e.size() < 65536 || (force && force[0] == 'l') || !libc_qsort_is_msort()) {
+    size_t min_n = 65536;                           // below this one thread is as fast
+    if (const char* m = getenv("WRT_KD_SORT_MIN")) min_n = (size_t)atoll(m);      // (tests lower it)
+    if (threads <= 1 || e.size() < min_n || (force && force[0] == 'l') || !libc_qsort_is_msort()) {
         qsort(e.data(), e.size(), sizeof(Event), compare_events);
         return;
     }
