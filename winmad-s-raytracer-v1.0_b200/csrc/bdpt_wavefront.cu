@@ -401,6 +401,7 @@ int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_para
     if (p->iter_first < 0 || p->iter_first >= p->iterations) { set_error("wrt_render_bdpt: iter_first out of range"); return WRT_ERR_INVALID; }
     P.iter_stride = stride;
     const int maxv = std::max(P.max_len - 1, 1);
+    if (maxv > 255) { set_error("wrt_render_bdpt: max_path_length > 256 is not supported (32-bit pair index of the connection kernel)"); return WRT_ERR_INVALID; }
     DevCamera dc; fill_camera(cam, dc);
 
     const int my_iters = (p->iterations - p->iter_first + stride - 1) / stride;

@@ -42,12 +42,11 @@ constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 #endif
 // Tail of a launch: once the global work counter is exhausted and a warp is down to its last rays, those are the rays that
 // decide when the launch ends — and on the scenes here they are long because of LEAF work (torus.scene: mean 20, p99.9 1300,
-// max 1500 primitive tests per ray).  With at most WRT_COOP_RAYS rays left the warp enters the tail loop, which stops giving one lane
-// to one ray: every ray inside a leaf gets a group of 32 / pow2ceil(rays) lanes that test as many records per pass (group_leaf_pass
-// below).  A SMALL launch (fewer work items than pool slots on the device, `share` below) enters it with up to 16 rays: its warps
-// are never full anyway, and 2 - 32 records per ray and pass beat 4 in sequence (torus.scene as shipped: 76 k rays per launch).
+// max 1500 primitive tests per ray).  With at most WRT_COOP_RAYS (16) rays left the warp enters the tail loop, which stops giving one
+// lane to one ray: every ray inside a leaf gets a group of 32 / pow2ceil(rays) lanes that test as many records per pass
+// (group_leaf_pass below) — 2 - 32 records per ray and pass beat 4 in sequence once the lanes cannot be filled anyway.
 #ifndef WRT_COOP_RAYS
-#define WRT_COOP_RAYS 4
+#define WRT_COOP_RAYS 16
 #endif
 #ifndef WRT_COOP_MIN_RECORDS
 #define WRT_COOP_MIN_RECORDS 8
@@ -57,12 +56,12 @@ constexpr unsigned kMinRefill = WRT_POOL_MIN_REFILL;
 // 3.78 ms alone, 400 ns per visit; prefetching the child pair into L1 changed nothing, profiles/r2_experiments.md).  Most of those
 // instructions were the two ring switches per leaf (store the state, re-queue, reload, cooperative pass, re-queue, reload).  In the
 // tail loop a node round therefore tests a SHORT leaf (< WRT_COOP_MIN_RECORDS records) right where it meets it — the same
-// leaf_record() steps in the same order — and runs WRT_TAIL_NODE_STEPS steps per ray instead of 6 (no other ray waits for the lanes).
+// leaf_record() steps in the same order — and runs WRT_TAIL_NODE_STEPS (48) steps per ray instead of 6 (no other ray waits for the lanes).
 #ifndef WRT_MIN_SHARE
 #define WRT_MIN_SHARE 8
 #endif
 #ifndef WRT_TAIL_NODE_STEPS
-#define WRT_TAIL_NODE_STEPS 24
+#define WRT_TAIL_NODE_STEPS 48
 #endif
 #ifndef WRT_TAIL_INLINE_LEAVES
 #define WRT_TAIL_INLINE_LEAVES 1
@@ -236,7 +235,7 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
             if (exhausted) break;
             continue;
         }
-        if (!TAIL && WRT_COOP_RAYS > 0 && exhausted && cn + cp <= (share < (unsigned)kPoolRays ? 16u : (unsigned)WRT_COOP_RAYS)) break;     // the tail loop takes over
+        if (!TAIL && WRT_COOP_RAYS > 0 && exhausted && cn + cp <= (unsigned)WRT_COOP_RAYS) break;     // the tail loop takes over
         if (TAIL && cp > 0u && cp >= cn && cp <= 16u) {
             // ---- cooperative leaf passes (tail loop): every ray of the prim ring gets a group of lanes (group_leaf_pass) --------
             const unsigned cnt = cp;
