@@ -77,6 +77,8 @@ struct alignas(16) int4 { int x, y, z, w; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r = { x, y, z, w }; return r; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 
+static std::atomic<unsigned long long> g_par_ok{0}, g_par_fallback{0};
+static inline void ws_par_count(bool ok) { if (ok) g_par_ok++; else g_par_fallback++; }
 #include "scene_layout.h"
 #include "trace_pooled.cuh"      // includes trace_persistent.cuh and traverse.cuh
 
@@ -167,6 +169,9 @@ void ws_trace_closest(void* hv, const wrt_ray* rays, size_t n, int pruned, int s
     WsClosestSrc src = { rays, prim, t };
     if (pruned) ws_run<true>(sc, src, n, sched); else ws_run<false>(sc, src, n, sched);
 }
+
+// whole-warp traversals of last rays since the last call: finished that way / handed back to the ordinary rounds
+void ws_par_stats(unsigned long long* out2) { out2[0] = g_par_ok.exchange(0); out2[1] = g_par_fallback.exchange(0); }
 
 void ws_trace_occluded(void* hv, const float* q9, size_t n, int pruned, int sched, uint8_t* occ)
 {

@@ -37,6 +37,13 @@ class WarpSim:
                                prim.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p))
         return prim, t
 
+    @staticmethod
+    def par_stats():
+        """(finished by the whole-warp traversal, handed back to the ordinary rounds) since the last call."""
+        out = (C.c_ulonglong * 2)()
+        lib().ws_par_stats(out)
+        return int(out[0]), int(out[1])
+
     def trace_occluded(self, q9, pruned=True, sched=3):
         q = np.ascontiguousarray(q9, np.float32).reshape(-1, 9)
         occ = np.full(len(q), 7, np.uint8)

@@ -218,17 +218,54 @@ def test_warpsim_schedulers_match_port(wrt, monkeypatch, sched):
         # of 2 ... 32 lanes in the leaves): closest hits and occlusion flags
         occ = port.occluded(q)
         want_r = port.intersect(rays)
+        ws.par_stats()
         for m in (3, 7, 40, 100, 230):
             for pruned in (True, False):
                 got = ws.trace_closest(rays[:m], pruned, 3)
                 assert np.array_equal(got[0], want_r[0][:m]) and np.array_equal(util.bits(got[1]), util.bits(want_r[1][:m])), (m, pruned)
             assert np.array_equal(ws.trace_occluded(q[:m], True, 3), occ[:m]), m
+        done, back = ws.par_stats()
+        print("whole-warp traversal of last rays: %d finished, %d handed back" % (done, back))
+        assert done > 20            # the path under test was taken (par_traverse), and its answers are the oracle's
     # golden primary rays of the fixture (a strided sample): the reference's own answers
     cam = wrt.Camera.from_ref_array(z["cam45"])
     prim_rays = wrt.generate_rays(cam, scenes.pixel_centres(512, 512, step=2))
     sel = np.arange(0, len(prim_rays), 53)[: n]
     got = ws.trace_closest(prim_rays[sel], True, sched)
     assert np.array_equal(got[0], z["P_prim"][sel]) and np.array_equal(util.bits(got[1]), util.bits(z["P_t"][sel]))
+
+
+def test_warpsim_whole_warp_traversal_of_last_rays(wrt, monkeypatch):
+    """par_traverse (trace_pooled.cuh): the last rays of a launch are traversed by the whole warp — sub-trees side by side, far children
+    handed to idle lanes, no acceptance rule, closest hit + runner-up; near-ties go back to the ordinary rounds.  Launches of one or
+    two rays put every ray through it: adversarial rays (vertex / edge hits = near-ties, axis-parallel = degenerate, spheres) on the
+    mixed golden scene with chunked leaves, PRUNED and EXACT, closest hits and occlusion flags — all must equal the oracle's."""
+    from warpsim_py import WarpSim
+    monkeypatch.setenv("WRT_LEAF_SKIP_MIN", "3"); monkeypatch.setenv("WRT_LEAF_SKIP_CHUNK", "2")
+    sc, z = scenes.load_fixture("mixed_torus")
+    hs = util.host_scene(wrt, sc)
+    ws = WarpSim(hs.desc(), hs)
+    port = engines.PortEngine(wrt, sc)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 260, seed=12))
+    short = rays.copy(); short[:, 7] = np.random.default_rng(2).uniform(0.05, 4.0, len(rays)).astype(np.float32)
+    ws.par_stats()
+    for rr in (rays, short):
+        want = port.intersect(rr)
+        for pruned in (True, False):
+            for i in range(0, len(rr), 2):
+                got = ws.trace_closest(rr[i:i + 2], pruned, 3)
+                assert np.array_equal(got[0], want[0][i:i + 2]) and np.array_equal(util.bits(got[1]), util.bits(want[1][i:i + 2])), (i, pruned)
+    done, back = ws.par_stats()
+    print("closest: %d rays finished by the whole warp, %d handed back (near-ties / the reference's tmax stop)" % (done, back))
+    assert done > 350 and back > 10
+    full = port.intersect(rays, full=True)
+    q = scenes.nee_queries(full[2], (full[0] >= 0) & (full[5] > 0), sc.lights)[:160]
+    occ = port.occluded(q)
+    for i in range(0, len(q), 2):
+        assert np.array_equal(ws.trace_occluded(q[i:i + 2], True, 3), occ[i:i + 2]), i
+    done, back = ws.par_stats()
+    print("occlusion: %d finished by the whole warp, %d handed back" % (done, back))
+    assert done > 60
 
 
 def test_warpsim_nan_interval_and_tiny_batches(wrt):

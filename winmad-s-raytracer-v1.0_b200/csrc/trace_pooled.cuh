@@ -155,6 +155,185 @@ __device__ __forceinline__ int group_leaf_pass(const DevSceneView& sc, Src& src,
     return decided ? 2 : (leaf_done ? 1 : 0);
 }
 
+
+// ---- one ray, the whole warp (tail loop, WRT_PAR_RAYS) ------------------------------------------------------------------------
+// What is left of a launch when everything else is done is the dependent chain of its longest rays: ~9 000 visits of ONE ray by a
+// warp that has nothing else to issue (C3: 3.2 ms for one grazing camera ray, profiles/r2_experiments.md).  The entries on a ray's
+// stack are independent sub-traversals — (node, tmin, tmax) is all the state the reference's loop carries into one — so the warp
+// runs them side by side: lane j starts with entry j, every lane walks its sub-tree with a private stack, and a lane that would
+// PUSH a far child hands it to an idle lane instead (ballot / rank matching once per step), so the work spreads as fast as the tree
+// branches.  What is NOT independent is the reference's acceptance rule `t - best < -EPS` applied in visit order: of two hits closer
+// than EPS the one visited first wins.  The lanes therefore do not apply it at all.  Each lane keeps the smallest hit it has seen
+// and the second smallest of a different primitive; at the end the warp has the closest hit t1 and the runner-up t2.  If
+// t2 - t1 >= 2 EPS the visit order cannot matter: whichever of the two the reference meets first, it ends with t1 (a later t1
+// replaces anything >= t1 + EPS, and nothing within EPS of t1 exists to be met first) — that primitive and its t (the same
+// Triangle::hit arithmetic, bit for bit) are the answer.  Otherwise (a hit on a shared edge: both neighbours within EPS), or if a
+// lane meets the reference's `ray.tmax < tmin` stop (KDtreeAccel.cpp:323, order dependent as well), or a private stack fills up,
+// the attempt is dropped: the ray's own state was never touched, it is marked and finishes in the ordinary rounds.
+// PRUNED skipping inside a lane uses the lane's own smallest hit, with a 2 EPS guard on rule (a) so that no hit within 2 EPS of the
+// final t1 can be skipped anywhere (rule (b) — the ray misses the box — is geometric and needs none).
+#ifndef WRT_PAR_RAYS
+#define WRT_PAR_RAYS 8
+#endif
+constexpr int kParDepth = 30;                                    // private stack entries per lane: rows 34..63 of the warp's scratch
+constexpr size_t kParBaseF4 = (size_t)34 * kPoolRays * sizeof(float2) / sizeof(float4);
+constexpr int kNoParBit = 1 << 28;                               // PoolSmem::d.w: this ray finishes in the ordinary rounds
+
+__device__ __forceinline__ unsigned nth_set_lane(unsigned mask, unsigned k)
+{
+    for (unsigned i = 0; i < k; i++) mask &= mask - 1u;
+    return (unsigned)__ffs(mask) - 1u;
+}
+
+struct ParHits { float m1, m2; int p1; };                        // smallest hit (t, primitive) and the second smallest t of another primitive
+__device__ __forceinline__ void par_offer(ParHits& H, float t, int prim)
+{
+    if (prim == H.p1) return;                                    // the same primitive listed by another leaf: the same t
+    if (t < H.m1) { H.m2 = H.m1; H.m1 = t; H.p1 = prim; }
+    else if (t < H.m2) H.m2 = t;
+}
+
+__device__ __forceinline__ bool par_box_prunable(float lox, float loy, float loz, float hix, float hiy, float hiz, const RayIn& r,
+                                                 float ix, float iy, float iz, const ParHits& H)
+{
+    float en, ex;
+    box_interval_regular(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz, en, ex);
+    if (H.p1 >= 0 && en > H.m1 * WRT_PRUNE_REL && en > H.m1 + 2.f * WRT_EPS) return true;
+    const float m = 1e-4f * (fabsf(en) + fabsf(ex)) + 1e-4f;
+    return (en > ex + m) || (ex < -m);
+}
+
+// Returns true when the ray was finished (src.done called, the slot is free); false = not decidable this way, state untouched
+// except for the kNoParBit mark.  Called by the whole warp, converged; the ray is regular (not degenerate) and waits for a node step.
+template <bool PRUNED, class Src>
+__device__ __forceinline__ bool par_traverse(const DevSceneView& sc, Src& src, PoolSmem& sm, unsigned slot, float4* __restrict__ gstack, unsigned lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const float4 a = sm.a[slot], b = sm.b[slot], c = sm.c[slot], d = sm.d[slot];
+    const int4 e = sm.e[slot];
+    RayIn r; r.ox = a.x; r.oy = a.y; r.oz = a.z; r.dx = a.w; r.dy = b.x; r.dz = b.y; r.tmin = b.z; r.tmax = b.w;
+    const float ix = c.x, iy = c.y, iz = c.z;
+    const int spw = __float_as_int(d.w);
+    const int sp0 = spw & 0xffff;
+    const bool pop0 = (spw >> 30) & 1;
+    const float2* col = reinterpret_cast<const float2*>(gstack) + slot;          // the ray's own stack: read only
+    float4* priv = gstack + kParBaseF4 + lane;                                     // private entry k at priv[k * 32]
+    ParHits H; H.m1 = WRT_INF; H.m2 = WRT_INF; H.p1 = -1;
+    if (e.x >= 0) { H.m1 = c.w; H.p1 = e.x; }                                      // the hit the ray already holds (every lane prunes with it)
+    // entries in pop order: the current node (unless the ray waits for a pop), then the stack from the top
+    const int total = sp0 + (pop0 ? 0 : 1);
+    bool active = false, abort = false;
+    int node = 0, psp = 0; float tmin = 0.f, tmax = 0.f;
+    for (int j = (int)lane; j < total; j += 32) {
+        int n_; float t0, t1;
+        if (!pop0 && j == 0) { n_ = __float_as_int(d.z); t0 = d.x; t1 = d.y; }
+        else {
+            const int k = sp0 - (pop0 ? j : j - 1);                                // stack entry k (1-based row), its tmax = t of the row below
+            const float2 q = col[(unsigned)k * (unsigned)kPoolRays], below = col[(unsigned)(k - 1) * (unsigned)kPoolRays];
+            n_ = __float_as_int(q.x); t0 = q.y; t1 = below.y;
+        }
+        if (!active) { node = n_; tmin = t0; tmax = t1; active = true; }
+        else { priv[(unsigned)psp * 32u] = make_float4(__int_as_float(n_), t0, t1, 0.f); ++psp; }
+    }
+    for (;;) {
+        bool want = false; int far_n = 0; float far_t = 0.f, far_tmax = 0.f;
+        bool need_pop = false;
+        if (active) {
+            if (r.tmax < tmin) abort = true;                                       // KDtreeAccel.cpp:323 ends the WHOLE traversal: order dependent
+            const float4* np = sc.nodes + 2 * (size_t)node;
+            const float4 na = __ldg(np);
+            bool skip = false;
+            if (PRUNED) {
+                const float4 nb = __ldg(np + 1);
+                skip = par_box_prunable(na.z, na.w, nb.x, nb.y, nb.z, nb.w, r, ix, iy, iz, H);
+            }
+            const unsigned packed = __float_as_uint(na.y);
+            const unsigned hi = packed >> 2;
+            if (skip) need_pop = true;
+            else if ((packed & 3u) == WRT_LEAF_TAG) {
+                int rec = __float_as_int(na.x);
+                const int end = rec + (int)hi;
+                while (rec < end) {
+                    const float4* rp = sc.leaf_recs + 3 * (size_t)rec;
+                    const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+                    const int kind = __float_as_int(r2.w);
+                    rec += 1;
+                    if (kind == WRT_REC_SKIP) {
+                        if (PRUNED && par_box_prunable(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r, ix, iy, iz, H)) rec += __float_as_int(r0.w);
+                        continue;
+                    }
+                    float t; bool hit;
+                    if (kind == 0) hit = triangle_t(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r, t);
+                    else {
+                        const float lo[3] = { r1.y, r1.z, r1.w }, hi3[3] = { r2.x, r2.y, r2.z };
+                        int inside;
+                        hit = sphere_t(r0.x, r0.y, r0.z, r1.x, lo, hi3, r, t, inside);
+                    }
+                    if (hit) par_offer(H, t, __float_as_int(r0.w));
+                }
+                need_pop = true;
+            } else {
+                const int axis = (int)(packed & 3u);
+                const float split = na.x;
+                const float o_a = sel3(axis, r.ox, r.oy, r.oz);
+                const float d_a = sel3(axis, r.dx, r.dy, r.dz);
+                const float i_a = sel3(axis, ix, iy, iz);
+                const float t = (split - o_a) * i_a;
+                const bool below_first = (o_a < split) || (o_a == split && d_a <= 0.f);
+                const int near_n = (int)hi + (below_first ? 0 : 1);
+                const int fn = (int)hi + (below_first ? 1 : 0);
+                const bool near_only = (t > tmax) || (t <= 0.f);
+                const bool far_only = !near_only && (t < tmin);
+                if (!near_only && !far_only) { want = true; far_n = fn; far_t = t; far_tmax = tmax; tmax = t; }
+                node = far_only ? fn : near_n;
+            }
+        }
+        // lanes that are out of work take over a far child another lane would push
+        const bool idle = !active || (need_pop && psp == 0);
+        const unsigned pm = __ballot_sync(FULL, want), im = __ballot_sync(FULL, idle);
+        const unsigned np_ = (unsigned)__popc(pm), ni = (unsigned)__popc(im);
+        const unsigned ri = (unsigned)__popc(im & lt), rp_ = (unsigned)__popc(pm & lt);
+        const bool take = idle && ri < np_;
+        const unsigned from = take ? nth_set_lane(pm, ri) : 0u;
+        const int g_n = __shfl_sync(FULL, far_n, from);
+        const float g_t = __shfl_sync(FULL, far_t, from), g_tm = __shfl_sync(FULL, far_tmax, from);
+        if (want && rp_ >= ni) {                                                   // nobody free: push on the private stack
+            if (psp >= kParDepth) abort = true;
+            else { priv[(unsigned)psp * 32u] = make_float4(__int_as_float(far_n), far_t, far_tmax, 0.f); ++psp; }
+        }
+        if (take) { node = g_n; tmin = g_t; tmax = g_tm; active = true; }
+        else if (need_pop || !active) {
+            if (psp > 0) { --psp; const float4 q = priv[(unsigned)psp * 32u]; node = __float_as_int(q.x); tmin = q.y; tmax = q.z; active = true; }
+            else active = false;
+        }
+        if (__any_sync(FULL, abort)) break;
+        if (!__any_sync(FULL, active)) break;
+    }
+    bool ok = !__any_sync(FULL, abort);
+    int res = -1; float best = WRT_INF;
+    if (ok) {
+        float g = H.m1;
+        for (int o = 16; o > 0; o >>= 1) g = fminf(g, __shfl_sync(FULL, g, (int)(lane ^ (unsigned)o)));
+        const unsigned wm = __ballot_sync(FULL, H.p1 >= 0 && H.m1 == g);
+        if (wm) {
+            res = __shfl_sync(FULL, H.p1, __ffs(wm) - 1);
+            best = g;
+            float s2 = (H.p1 >= 0 && H.p1 != res) ? H.m1 : H.m2;
+            for (int o = 16; o > 0; o >>= 1) s2 = fminf(s2, __shfl_sync(FULL, s2, (int)(lane ^ (unsigned)o)));
+            if (s2 - g < 2.f * WRT_EPS) ok = false;                               // two hits the reference's order-dependent rule has to separate
+        }
+    }
+    if (lane == 0) {
+        if (ok) src.done((size_t)(unsigned)e.w, r, res, (res >= 0) ? best : WRT_INF);
+        else sm.d[slot].w = __int_as_float(spw | kNoParBit);
+#ifdef WRT_WARPSIM
+        ws_par_count(ok);          // (CPU emulation only: the tests check that this path was taken)
+#endif
+    }
+    return ok;
+}
+
 struct PoolRings { unsigned hn, tn, hp, tp, hf, tf; };     // ring heads / tails (monotonic), warp-uniform
 
 // The scheduler loop.  TAIL = false: the steady state described at the top of this file; it returns as soon as the global
@@ -236,6 +415,20 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
             continue;
         }
         if (!TAIL && WRT_COOP_RAYS > 0 && exhausted && cn + cp <= (unsigned)WRT_COOP_RAYS) break;     // the tail loop takes over
+        if (TAIL && WRT_PAR_RAYS > 0 && WRT_STACK8 && cp == 0u && cn <= (unsigned)WRT_PAR_RAYS) {
+            // ---- the last rays: one ray, the whole warp (par_traverse) ----------------------------------------------------------
+            const unsigned slot = sm.ring[0][hn & RM];
+            const int spw = __float_as_int(sm.d[slot].w);
+            if (!(spw & kNoParBit) && !((spw >> 29) & 1)) {            // not marked for the ordinary rounds, not degenerate
+                hn += 1;
+                __syncwarp();
+                const bool ok = par_traverse<PRUNED>(sc, src, sm, slot, gstack, lane);
+                if (lane == 0) sm.ring[ok ? 2 : 0][(ok ? tf : tn) & RM] = (unsigned char)slot;
+                if (ok) tf += 1; else tn += 1;
+                __syncwarp();
+                continue;
+            }
+        }
         if (TAIL && cp > 0u && cp >= cn && cp <= 16u) {
             // ---- cooperative leaf passes (tail loop): every ray of the prim ring gets a group of lanes (group_leaf_pass) --------
             const unsigned cnt = cp;
@@ -405,7 +598,7 @@ __device__ __forceinline__ void pooled_loop(const DevSceneView& sc, Src& src, un
                 if (next == 2) {
                     src.done((size_t)(unsigned)sm.e[slot].w, r, T.res, (T.res >= 0) ? T.best : WRT_INF);
                 } else {
-                    sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(T.node), __int_as_float(T.sp | (T.degen ? (1 << 29) : 0) | (need_pop ? (1 << 30) : 0)));
+                    sm.d[slot] = make_float4(T.tmin, T.tmax, __int_as_float(T.node), __int_as_float(T.sp | (T.degen ? (1 << 29) : 0) | (need_pop ? (1 << 30) : 0) | (spw & kNoParBit)));
                     if (next == 1) { sm.e[slot].y = leaf_first; sm.e[slot].z = leaf_end; }
                     if (TAIL && WRT_TAIL_INLINE_LEAVES) { sm.c[slot].w = T.best; sm.e[slot].x = T.res; }      // (leaves tested in this round)
                 }
