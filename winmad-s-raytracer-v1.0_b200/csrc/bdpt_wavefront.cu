@@ -367,6 +367,7 @@ static int bdpt_batch(const wrt_bdpt_params* p)
 
 int render_bdpt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_bdpt_params* p, float* d_film, cudaStream_t st)
 {
+    NvtxRange nvtx_range("wrt: BDPT wavefront");
     if (!cam || !p || p->width <= 0 || p->height <= 0 || p->iterations <= 0 || p->max_path_length < 1) {
         set_error("wrt_render_bdpt: bad parameters"); return WRT_ERR_INVALID;
     }

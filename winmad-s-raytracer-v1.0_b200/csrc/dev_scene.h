@@ -94,7 +94,15 @@ struct wrt_scene {
     struct wrt_wavefront* wf_extra[7]; // further PT sub-pools (each with its own stream), see pt_wavefront.cu
 };
 
+#include <nvtx3/nvToolsExt.h>
 namespace wrt {
+// NVTX range around the host side of a library call (tracing); free when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 void set_error(const std::string& s);
 int cuda_fail(cudaError_t e, const char* what);
 #define WRT_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return wrt::cuda_fail(e__, #call); } while (0)

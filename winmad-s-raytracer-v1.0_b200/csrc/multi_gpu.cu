@@ -47,6 +47,7 @@ __global__ void k_film_sum_peers(float* __restrict__ dst, PeerFilms peers, int n
 // replica 0's film.  `floats` = film size; n_units = spp (PT) / iterations (BDPT): devices beyond n_units stay idle.
 int multi_render(wrt_scene* sc, size_t floats, int n_units, const std::function<int(wrt_scene*, int, int, float*)>& fn, float** film0)
 {
+    NvtxRange nvtx_range("wrt: multi-GPU render (replicas + film exchange)");
     const int n_dev = 1 + sc->n_replicas;
     const int n_active = std::max(1, std::min(n_dev, n_units));
     std::vector<int> rc(n_active, WRT_OK);

@@ -469,6 +469,7 @@ static int whitted_pending(wrt_wavefront* wf, int levels, WhittedPending& out)
 
 int render_pt_device(wrt_scene* sc, const wrt_camera* cam, const wrt_pt_params* p, float* d_film, cudaStream_t st, bool whitted)
 {
+    NvtxRange nvtx_range("wrt: PT / Whitted wavefront");
     if (!cam) { set_error("wrt_render_pt: null camera"); return WRT_ERR_INVALID; }
     if (sc->view.n_lights <= 0) { set_error("wrt_render_pt: the scene has no light (the reference indexes an empty vector here)"); return WRT_ERR_INVALID; }
     PtParams P;

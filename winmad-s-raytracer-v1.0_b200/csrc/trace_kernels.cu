@@ -241,6 +241,7 @@ int trace_ctx_for(wrt_scene* sc, cudaStream_t st, unsigned long long** counter, 
 static int launch_closest(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_t* d_prim, float* d_t,
                           float* d_p, float* d_n, int32_t* d_inside, int32_t* d_matid, cudaStream_t st)
 {
+    NvtxRange nvtx_range("wrt: trace closest");
     if (n == 0) return WRT_OK;
     unsigned long long* ctr; float4* scr;
     { int rc = trace_ctx_for(sc, st, &ctr, &scr); if (rc) return rc; }
@@ -260,6 +261,7 @@ static int launch_closest(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_
 
 static int launch_occluded(wrt_scene* sc, const float* d_q9, size_t n, uint8_t* d_occ, cudaStream_t st)
 {
+    NvtxRange nvtx_range("wrt: trace occluded");
     if (n == 0) return WRT_OK;
     unsigned long long* ctr; float4* scr;
     { int rc = trace_ctx_for(sc, st, &ctr, &scr); if (rc) return rc; }
