@@ -503,11 +503,13 @@ struct Builder {
         return node_off;
     }
 
-    // Same tree, the two sub-trees of the top `levels` levels built concurrently into private arrays and spliced
-    // back in pre-order (node, left sub-tree, right sub-tree): identical output to build().
-    void build_parallel(BuildNode* nd, int dep, FlatTree& out, int levels) const
+    // Same tree, the two sub-trees of every node with more than `task_objs` objects built concurrently into private arrays and
+    // spliced back in pre-order (node, left sub-tree, right sub-tree): identical output to build().  Tasks are cut by SIZE, not by
+    // depth: the reference's SAH peels thin slabs off the big scenes first (C5: 112 482 | 10 102 328 objects at the root), and a
+    // depth rule would spend its levels on those.
+    void build_parallel(BuildNode* nd, int dep, FlatTree& out, size_t task_objs) const
     {
-        if (levels <= 0 || nd->objs.size() < 4096) { build(nd, dep, out); return; }
+        if (nd->objs.size() <= task_objs || nd->objs.size() < 4096) { build(nd, dep, out); return; }
         int axis; Real split; BuildNode* l; BuildNode* r;
         const int n = (int)nd->objs.size();
         const auto t0 = std::chrono::steady_clock::now();
@@ -523,8 +525,8 @@ struct Builder {
         delete nd;
         FlatTree lt, rt;
         lt.depth = rt.depth = 0;
-        std::future<void> fl = std::async(std::launch::async, [&] { build_parallel(l, dep + 1, lt, levels - 1); });
-        build_parallel(r, dep + 1, rt, levels - 1);
+        std::future<void> fl = std::async(std::launch::async, [&] { build_parallel(l, dep + 1, lt, task_objs); });
+        build_parallel(r, dep + 1, rt, task_objs);
         fl.get();
         const int me = (int)out.axis.size();
         out.axis.push_back(axis); out.split.push_back(split);
@@ -612,9 +614,9 @@ bool build_kdtree(HostScene& hs, std::string& err)
     if (const char* e = getenv("WRT_KD_CHUNK_MIN")) chunk_min = (size_t)atoll(e);     // tests lower it to exercise the path
     Builder b = { boxes, hs.tree.dep_max, threads, chunk_min };
     if (threads > 1) {
-        int levels = 1;
-        while ((1 << levels) < 2 * threads && levels < 7) levels++;   // ~2 tasks per thread
-        b.build_parallel(root, 1, hs.tree, levels);
+        size_t task_objs = (size_t)n / (size_t)(4 * threads) + 1;     // ~4 tasks per thread by size
+        if (const char* e = getenv("WRT_KD_TASK_OBJS")) task_objs = (size_t)atoll(e);
+        b.build_parallel(root, 1, hs.tree, task_objs);
     } else {
         b.build(root, 1, hs.tree);
     }
