@@ -184,6 +184,7 @@ int wrt_get_stats(wrt_scene* sc, wrt_stats* out);
 int wrt_reset_stats(wrt_scene* sc);
 
 /* ---- level 1: ray queries (R/src/scene/scene.h:44-50) ------------------------------------------------ */
+/* One call traces at most 2^31 - 1 rays / queries (WRT_ERR_INVALID beyond that: split the batch). */
 /* Geometry* Scene::intersect(const Ray&, Intersection&)   scene.cpp:21-43.
  * prim[i] = index in Scene::objs or -1; t[i] = inter.t (INF=1e7 on a miss). Host buffers. */
 int wrt_trace_closest(wrt_scene* sc, const wrt_ray* rays, size_t n, int32_t* prim, float* t);

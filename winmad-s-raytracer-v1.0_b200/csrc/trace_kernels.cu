@@ -237,12 +237,20 @@ int trace_ctx_for(wrt_scene* sc, cudaStream_t st, unsigned long long** counter, 
     return WRT_OK;
 }
 
+// The pooled scheduler keeps a work item's index in 32 bits (PoolSmem::e.w): one call traces fewer than 2^31 rays (64 GB of wrt_ray).
+static int check_batch(size_t n, const char* who)
+{
+    if (n > (size_t)0x7fffffff) { set_error(std::string(who) + ": at most 2^31 - 1 rays per call (split the batch)"); return WRT_ERR_INVALID; }
+    return WRT_OK;
+}
+
 // d_counters layout: [0] work counter, [8..11] visit sums
 static int launch_closest(wrt_scene* sc, const wrt_ray* d_rays, size_t n, int32_t* d_prim, float* d_t,
                           float* d_p, float* d_n, int32_t* d_inside, int32_t* d_matid, cudaStream_t st)
 {
     NvtxRange nvtx_range("wrt: trace closest");
     if (n == 0) return WRT_OK;
+    { int rc = check_batch(n, "wrt_trace_closest"); if (rc) return rc; }
     unsigned long long* ctr; float4* scr;
     { int rc = trace_ctx_for(sc, st, &ctr, &scr); if (rc) return rc; }
     WRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
@@ -263,6 +271,7 @@ static int launch_occluded(wrt_scene* sc, const float* d_q9, size_t n, uint8_t* 
 {
     NvtxRange nvtx_range("wrt: trace occluded");
     if (n == 0) return WRT_OK;
+    { int rc = check_batch(n, "wrt_trace_occluded"); if (rc) return rc; }
     unsigned long long* ctr; float4* scr;
     { int rc = trace_ctx_for(sc, st, &ctr, &scr); if (rc) return rc; }
     WRT_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), st));
@@ -331,6 +340,7 @@ int wrt_trace_any(wrt_scene* sc, const wrt_ray* rays, size_t n, uint8_t* hit)
     CHECK_SCENE(sc);
     if (n == 0) return WRT_OK;
     if (!rays || !hit) { set_error("wrt_trace_any: null buffer"); return WRT_ERR_INVALID; }
+    { int rc0 = check_batch(n, "wrt_trace_any"); if (rc0) return rc0; }
     int rc = ensure_scratch(sc, n * sizeof(wrt_ray), n);
     if (rc) return rc;
     cudaStream_t st = sc->stream;
@@ -358,6 +368,7 @@ int wrt_trace_shadow(wrt_scene* sc, const wrt_ray* rays, const float* target3, s
     CHECK_SCENE(sc);
     if (n == 0) return WRT_OK;
     if (!rays || !target3 || !visible) { set_error("wrt_trace_shadow: null buffer"); return WRT_ERR_INVALID; }
+    { int rc0 = check_batch(n, "wrt_trace_shadow"); if (rc0) return rc0; }
     int rc = ensure_scratch(sc, n * (sizeof(wrt_ray) + 16), n * 4);  // rays, then targets (16-byte aligned start)
     if (rc) return rc;
     cudaStream_t st = sc->stream;
