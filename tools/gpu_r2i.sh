@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, ninth GPU call: ray suspension — full parity suite, then tail-budget A/B on C1 / C3@8spp / C3 / torus / c5_small
+# (historical: WRT_TAIL_BUDGET drove the ray-suspension experiment, whose code was removed again — commit 1f02113, profiles/r2_experiments.md)
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q -x -s > gpurun_out/pytest_gpu_r2i.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|handed over" gpurun_out/pytest_gpu_r2i.log | tail -4
 one() { # label workload spp steps env...

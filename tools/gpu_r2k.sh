@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, tenth GPU call: ray suspension with the priority run — parity of the PT tests, then tail-budget A/B
+# (historical: WRT_TAIL_BUDGET drove the ray-suspension experiment, whose code was removed again — commit 1f02113, profiles/r2_experiments.md)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_render.py tests/test_gpu_tape.py -m gpu -q -x -s -k "pt or PT or suspension" > gpurun_out/pytest_gpu_r2k.log 2>&1; echo "pytest rc=$?"; grep -a -E "passed|failed|handed over" gpurun_out/pytest_gpu_r2k.log | tail -4
 one() { # label workload spp steps env...
