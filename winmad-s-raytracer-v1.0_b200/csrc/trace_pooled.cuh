@@ -11,7 +11,7 @@
 // The per-ray steps are exactly those of traverse.cuh / trace_persistent.cuh (trav_begin, trav_skip,
 // trav_interior arithmetic, leaf_record, pop), executed in the same order for every ray, so results are
 // bit-identical to kd_traverse().  Only the traversal stack moves: it lives in a per-warp global
-// scratch area ([depth][slot], 16-byte entries) because any lane may continue any ray.
+// scratch area ([depth][slot], 8-byte entries above a sentinel row: WRT_STACK8 below) because any lane may continue any ray.
 #pragma once
 #include "trace_persistent.cuh"
 
