@@ -250,6 +250,27 @@ def test_empty_ragged_and_device_pointer_variants(wrt):
     assert np.array_equal(d_prim.cpu().numpy(), b[0]) and np.array_equal(util.bits(d_t.cpu().numpy()), util.bits(b[1]))
 
 
+@pytest.mark.gpu
+def test_small_launches_through_the_pooled_scheduler(wrt):
+    """Launches of 1 ... 3 000 rays on a tree large enough for the pooled scheduler (torus.scene, 11 429 nodes): even-share refill,
+    tail loop from the first round, lane groups in the leaves, whole-warp traversal of the last rays — closest hits (PRUNED and EXACT)
+    and occlusion flags must equal the oracle's bit for bit.  (GPU twin of the warp-simulator tests in tests/test_hostsim.py.)"""
+    sc, z = scenes.load_fixture("torus")
+    port = engines.PortEngine(wrt, sc)
+    rays = wrt.make_rays(engines.adversarial_rays(sc, 3000, seed=21))
+    want = port.intersect(rays)
+    full = port.intersect(rays, full=True)
+    q = scenes.nee_queries(full[2], (full[0] >= 0) & (full[5] > 0), sc.lights)
+    occ = port.occluded(q)
+    for pruned in (True, False):
+        cuda = engines.CudaEngine(wrt, sc, pruned)
+        for m in (1, 2, 7, 40, 230, 3000):
+            got = cuda.intersect(rays[:m])
+            assert np.array_equal(got[0], want[0][:m]) and np.array_equal(util.bits(got[1]), util.bits(want[1][:m])), (pruned, m)
+            k = min(m, len(q))
+            assert np.array_equal(cuda.occluded(q[:k]), occ[:k]), (pruned, m)
+
+
 # ---- round 2: the two query flavours that were only self-tested, and the grazing-ray class -------------------------------
 @pytest.mark.parametrize("name", ["torus", "small_mixed", "synthetic"])
 def test_shadow_and_any_queries_vs_oracle(wrt, have_ref, name):
