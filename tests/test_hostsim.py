@@ -268,6 +268,28 @@ def test_warpsim_whole_warp_traversal_of_last_rays(wrt, monkeypatch):
     assert done > 60
 
 
+def test_warpsim_whole_warp_traversal_on_edge_scenes(wrt):
+    """par_traverse on the degenerate inputs of scenes.edge_scenes() — duplicated triangles (two primitives with the SAME t: the
+    runner-up test must send them back to the ordinary rounds, where the first one listed wins), zero-area triangles, a sliver,
+    mixed magnitudes, a sphere in a triangle soup: launches of two rays, closest hits == oracle."""
+    from warpsim_py import WarpSim
+    ws_done = ws_back = 0
+    for sc in scenes.edge_scenes():
+        hs = util.host_scene(wrt, sc)
+        ws = WarpSim(hs.desc(), hs)
+        port = engines.PortEngine(wrt, sc)
+        with np.errstate(all="ignore"):
+            rays = wrt.make_rays(engines.adversarial_rays(sc, 80, seed=5))
+        want = port.intersect(rays)
+        ws.par_stats()
+        for i in range(0, len(rays), 2):
+            got = ws.trace_closest(rays[i:i + 2], True, 3)
+            assert np.array_equal(got[0], want[0][i:i + 2]) and np.array_equal(util.bits(got[1]), util.bits(want[1][i:i + 2])), (sc.name, i)
+        d, b = ws.par_stats(); ws_done += d; ws_back += b
+    print("edge scenes: %d rays finished by the whole warp, %d handed back" % (ws_done, ws_back))
+    assert ws_done > 100 and ws_back > 0
+
+
 def test_warpsim_nan_interval_and_tiny_batches(wrt):
     """Pooled scheduler on the CPU: the NaN-interval regression rays (tests above) and batches smaller than a warp / than the
     refill threshold (1, 5, 33 rays) — exhaustion and partially filled rings."""
