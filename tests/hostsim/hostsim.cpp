@@ -69,6 +69,18 @@ void hs_debug_shading(void* hv, const wrt_camera* cam, int what, int iparam, con
 int hs_num_nodes(void* h) { return ((HsScene*)h)->L.n_nodes; }
 long long hs_num_recs(void* h) { return ((HsScene*)h)->L.n_recs; }
 
+// FNV-1a over the bytes of the node, leaf-record and primitive arrays of the layout (serial = parallel build_layout test)
+unsigned long long hs_layout_digest(void* hv)
+{
+    const SceneLayout& L = ((HsScene*)hv)->L;
+    unsigned long long h = 1469598103934665603ull;
+    auto eat = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+    eat(L.nodes.data(), L.nodes.size() * sizeof(float4));
+    eat(L.recs.data(), L.recs.size() * sizeof(float4));
+    eat(L.prims.data(), L.prims.size() * sizeof(float4));
+    return h;
+}
+
 void hs_trace_closest(void* hv, const wrt_ray* rays, size_t n, int pruned, int32_t* prim, float* t)
 {
     const DevSceneView& sc = ((HsScene*)hv)->L.view;

@@ -37,6 +37,11 @@ class HostSim:
     def num_recs(self):
         return int(lib().hs_num_recs(self.h))
 
+    def layout_digest(self):
+        f = lib().hs_layout_digest
+        f.restype = C.c_ulonglong
+        return int(f(self.h))
+
     def trace_closest(self, rays8, pruned=True):
         r = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)
         prim = np.zeros(len(r), np.int32); t = np.zeros(len(r), np.float32)

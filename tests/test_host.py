@@ -58,6 +58,24 @@ def test_parallel_kd_build_equals_serial(wrt, monkeypatch):
         assert np.array_equal(util.bits(a["root_box"]), util.bits(b["root_box"]))
 
 
+def test_parallel_layout_equals_serial(wrt, monkeypatch):
+    """build_layout (csrc/scene_layout.cpp) on threads writes the same bytes as on one: node array, leaf records incl. skip records,
+    primitive table — on a mesh + spheres scene with every leaf >= 3 entries chunked."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+    from hostsim_py import HostSim
+    monkeypatch.setenv("WRT_LEAF_SKIP_MIN", "3"); monkeypatch.setenv("WRT_LEAF_SKIP_CHUNK", "2")
+    sc = scenes.synthetic_torus_scene(n=160, width=64, height=64, n_spheres=3000)
+    hs = util.host_scene(wrt, sc)
+    monkeypatch.setenv("WRT_LAYOUT_THREADS", "1")
+    a = HostSim(hs.desc(), hs)
+    want, nrec = a.layout_digest(), a.num_recs()
+    for t in ("2", "7", "16"):
+        monkeypatch.setenv("WRT_LAYOUT_THREADS", t)
+        b = HostSim(hs.desc(), hs)
+        assert b.num_recs() == nrec and b.layout_digest() == want, t
+
+
 def _eps_dense_scene(n=64, scale=0.004):
     """A mesh whose box bounds lie closer together than the reference's EPS (1e-3): the displaced torus scaled down until a triangle is
     ~1e-4 across.  Long chains of event positions are then pairwise "equal" under cmp(), the comparator is as non-transitive as it gets,

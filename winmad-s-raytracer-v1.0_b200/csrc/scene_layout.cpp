@@ -19,11 +19,35 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
 #include "scene_layout.h"
 
 namespace wrt {
 
 namespace {
+
+// The per-primitive and per-leaf phases of build_layout write disjoint ranges: they run on threads (WRT_LAYOUT_THREADS, default = the
+// machine's, at most 16; 1 = serial) and produce the same bytes (tests/test_host.py::test_parallel_layout_equals_serial).
+int layout_threads(size_t work)
+{
+    int t = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("WRT_LAYOUT_THREADS")) t = atoi(e);
+    if (t > 16) t = 16;
+    if (t < 1 || work < 50000) t = 1;
+    return t;
+}
+
+template <class F>
+void parallel_ranges(int n, int threads, F fn)      // fn(i0, i1) over [0, n) cut into `threads` ranges
+{
+    if (threads <= 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back([=, &fn] { fn((int)((long long)n * t / threads), (int)((long long)n * (t + 1) / threads)); });
+    fn(0, (int)((long long)n / threads));
+    for (auto& x : th) x.join();
+}
 
 inline float as_float(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
 inline float as_float_u(uint32_t v) { float f; memcpy(&f, &v, 4); return f; }
@@ -196,37 +220,45 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
 
     std::vector<float> pboxes((size_t)d->n_prims * 6);  // reference prim boxes (spheres need theirs in hit())
     std::vector<float> cons((size_t)d->n_prims * 6);    // conservative boxes, rounded outward
-    for (int i = 0; i < d->n_prims; i++) {
-        const float* pd = d->prim_data + 9 * (size_t)i;
-        if (d->prim_kind[i] != WRT_PRIM_TRIANGLE && d->prim_kind[i] != WRT_PRIM_SPHERE) {
-            set_error("unknown primitive kind"); return false;
+    const int nthr = layout_threads((size_t)d->n_prims + (size_t)n_recs);
+    std::atomic<int> bad(0);            // 1 unknown kind, 2 material id, 3 light id, 4 primitive reference, 5 record plan
+    parallel_ranges(d->n_prims, nthr, [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++) {
+            const float* pd = d->prim_data + 9 * (size_t)i;
+            if (d->prim_kind[i] != WRT_PRIM_TRIANGLE && d->prim_kind[i] != WRT_PRIM_SPHERE) { bad = 1; return; }
+            // the shaders index materials[matid] / lights[-matid-1] directly (the reference reads out of bounds here)
+            const int m = d->prim_matid[i];
+            if (m > 0 && m >= d->n_materials) { bad = 2; return; }
+            if (m < 0 && (-(int64_t)m - 1) >= d->n_lights) { bad = 3; return; }
+            float* b = &pboxes[6 * (size_t)i];
+            if (d->prim_kind[i] == WRT_PRIM_SPHERE) {  // Sphere::setBox + AABB::extend
+                for (int a = 0; a < 3; a++) { b[a] = pd[a] - pd[3]; b[3 + a] = pd[a] + pd[3]; }
+                for (int a = 0; a < 3; a++) { float df = b[a] - b[3 + a]; if (!(df < -WRT_EPS) && !(df > WRT_EPS)) b[3 + a] += 10 * WRT_EPS; }
+            }
+            double lo[3], hi[3];
+            conservative_box(d->prim_kind[i], pd, lo, hi);
+            for (int a = 0; a < 3; a++) { cons[6 * (size_t)i + a] = round_down(lo[a]); cons[6 * (size_t)i + 3 + a] = round_up(hi[a]); }
         }
-        // the shaders index materials[matid] / lights[-matid-1] directly (the reference reads out of bounds here)
-        const int m = d->prim_matid[i];
-        if (m > 0 && m >= d->n_materials) { set_error("primitive material id past the material table"); return false; }
-        if (m < 0 && (-(int64_t)m - 1) >= d->n_lights) { set_error("emitter primitive refers to a light past the light table"); return false; }
-        float* b = &pboxes[6 * (size_t)i];
-        if (d->prim_kind[i] == WRT_PRIM_SPHERE) {  // Sphere::setBox + AABB::extend
-            for (int a = 0; a < 3; a++) { b[a] = pd[a] - pd[3]; b[3 + a] = pd[a] + pd[3]; }
-            for (int a = 0; a < 3; a++) { float df = b[a] - b[3 + a]; if (!(df < -WRT_EPS) && !(df > WRT_EPS)) b[3 + a] += 10 * WRT_EPS; }
-        }
-        double lo[3], hi[3];
-        conservative_box(d->prim_kind[i], pd, lo, hi);
-        for (int a = 0; a < 3; a++) { cons[6 * (size_t)i + a] = round_down(lo[a]); cons[6 * (size_t)i + 3 + a] = round_up(hi[a]); }
-    }
+    });
+    if (bad == 1) { set_error("unknown primitive kind"); return false; }
+    if (bad == 2) { set_error("primitive material id past the material table"); return false; }
+    if (bad == 3) { set_error("emitter primitive refers to a light past the light table"); return false; }
 
     std::vector<float4> recs((size_t)n_recs * 3);
     std::vector<float> nb((size_t)n_live * 6);  // node bounds
     for (int i = 0; i < n_live; i++) for (int a = 0; a < 3; a++) { nb[6 * (size_t)i + a] = INFINITY; nb[6 * (size_t)i + 3 + a] = -INFINITY; }
-    for (int i = 0; i < n_live; i++) {
+    // every leaf writes its own run of records and its own bounds: node ranges on threads
+    parallel_ranges(n_live, nthr, [&](int n0, int n1) {
+    std::vector<int> chunks;
+    for (int i = n0; i < n1; i++) {
         const int o = order[i];
         if (T.axis[o] != -1) continue;
         const int c = T.n_ref[o];
         for (int k = 0; k < c; k++) {
             const int p = T.refs[T.first_ref[o] + k];
-            if (p < 0 || p >= d->n_prims) { set_error("leaf references a primitive out of range"); return false; }
+            if (p < 0 || p >= d->n_prims) { bad = 4; return; }
         }
-        std::vector<int> chunks; int per_group;
+        chunks.clear(); int per_group;
         plan_leaf(c, skips, chunks, per_group);
         int64_t pos = first_rec[i];
         auto emit_prim = [&](int k) {
@@ -276,8 +308,11 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
                 j += in_group;
             }
         }
-        if (pos != first_rec[i] + leaf_recs_n[i]) { set_error("internal: leaf record plan mismatch"); return false; }
+        if (pos != first_rec[i] + leaf_recs_n[i]) { bad = 5; return; }
     }
+    });
+    if (bad == 4) { set_error("leaf references a primitive out of range"); return false; }
+    if (bad == 5) { set_error("internal: leaf record plan mismatch"); return false; }
     for (int i = n_live - 1; i >= 0; i--) {  // children have larger indices than parents
         const int o = order[i];
         if (T.axis[o] == -1) continue;
@@ -291,18 +326,21 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
     }
 
     std::vector<float4> nodes((size_t)n_live * 2);
-    for (int i = 0; i < n_live; i++) {
-        const int o = order[i];
-        float x, y;
-        if (T.axis[o] == -1) { x = as_float((int32_t)first_rec[i]); y = as_float_u(((uint32_t)leaf_recs_n[i] << 2) | WRT_LEAF_TAG); }
-        else { x = T.split[o]; y = as_float_u(((uint32_t)pair_of[o] << 2) | (uint32_t)T.axis[o]); }
-        const float* b = &nb[6 * (size_t)i];
-        nodes[2 * (size_t)i] = make_float4(x, y, b[0], b[1]);
-        nodes[2 * (size_t)i + 1] = make_float4(b[2], b[3], b[4], b[5]);
-    }
+    parallel_ranges(n_live, nthr, [&](int n0, int n1) {
+        for (int i = n0; i < n1; i++) {
+            const int o = order[i];
+            float x, y;
+            if (T.axis[o] == -1) { x = as_float((int32_t)first_rec[i]); y = as_float_u(((uint32_t)leaf_recs_n[i] << 2) | WRT_LEAF_TAG); }
+            else { x = T.split[o]; y = as_float_u(((uint32_t)pair_of[o] << 2) | (uint32_t)T.axis[o]); }
+            const float* b = &nb[6 * (size_t)i];
+            nodes[2 * (size_t)i] = make_float4(x, y, b[0], b[1]);
+            nodes[2 * (size_t)i + 1] = make_float4(b[2], b[3], b[4], b[5]);
+        }
+    });
 
     std::vector<float4> prims((size_t)d->n_prims * 3);
-    for (int i = 0; i < d->n_prims; i++) {
+    parallel_ranges(d->n_prims, nthr, [&](int i0, int i1) {
+    for (int i = i0; i < i1; i++) {
         const float* pd = d->prim_data + 9 * (size_t)i;
         if (d->prim_kind[i] == WRT_PRIM_TRIANGLE) {
             prims[3 * (size_t)i] = make_float4(pd[0], pd[1], pd[2], as_float(d->prim_matid[i]));
@@ -314,6 +352,7 @@ bool build_layout(const wrt_scene_desc* d, SceneLayout& L, std::string& err)
             prims[3 * (size_t)i + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
+    });
 
     std::vector<DevMaterial> mats(std::max(d->n_materials, 1));
     memset(mats.data(), 0, mats.size() * sizeof(DevMaterial));
